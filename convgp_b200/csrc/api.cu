@@ -1,0 +1,444 @@
+// C-ABI entry points of libconvgp_b200.so: validation, path selection, launch configuration.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "fast.cuh"
+#include "generic.cuh"
+
+namespace cgp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return CGP_ERR_CUDA;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+struct Geo {
+  int Hout, Wout, Pc, P, D;
+};
+
+static int geometry(const cgp_kernel_desc* d, Geo* g) {
+  if (!d) {
+    set_error("descriptor is NULL");
+    return CGP_ERR_BAD_DESC;
+  }
+  if (d->dtype != CGP_F32 && d->dtype != CGP_F64) {
+    set_error("dtype %d is not CGP_F32/CGP_F64", d->dtype);
+    return CGP_ERR_BAD_DESC;
+  }
+  if (d->H <= 0 || d->W <= 0 || d->C <= 0 || d->ph <= 0 || d->pw <= 0 || d->ph > d->H || d->pw > d->W) {
+    set_error("bad image/patch geometry H=%d W=%d C=%d ph=%d pw=%d", d->H, d->W, d->C, d->ph, d->pw);
+    return CGP_ERR_BAD_DESC;
+  }
+  if (d->layout != CGP_LAYOUT_PLANAR && d->layout != CGP_LAYOUT_COLOUR_PATCH) {
+    set_error("bad layout %d", d->layout);
+    return CGP_ERR_BAD_DESC;
+  }
+  if (d->out_mode != CGP_OUT_SUM && d->out_mode != CGP_OUT_PER_CHANNEL) {
+    set_error("bad out_mode %d", d->out_mode);
+    return CGP_ERR_BAD_DESC;
+  }
+  if (d->out_mode == CGP_OUT_PER_CHANNEL && d->layout != CGP_LAYOUT_PLANAR) {
+    set_error("per-channel output needs the planar (Conv) patch layout");
+    return CGP_ERR_BAD_DESC;
+  }
+  if (d->n_groups < 1) {
+    set_error("n_groups must be >= 1");
+    return CGP_ERR_BAD_DESC;
+  }
+  g->Hout = d->H - d->ph + 1;
+  g->Wout = d->W - d->pw + 1;
+  g->Pc = g->Hout * g->Wout;
+  if (d->layout == CGP_LAYOUT_PLANAR) {
+    g->P = g->Pc * d->C;
+    g->D = d->ph * d->pw;
+  } else {
+    g->P = g->Pc;
+    g->D = d->ph * d->pw * d->C;
+  }
+  if ((long long)d->n_groups * g->D > kMaxMask) {
+    set_error("n_groups*D = %lld exceeds %d", (long long)d->n_groups * g->D, kMaxMask);
+    return CGP_ERR_UNSUPPORTED;
+  }
+  return CGP_OK;
+}
+
+static bool mask_at(const cgp_kernel_desc* d, int D, int g, int dim) {
+  return d->active ? d->active[(size_t)g * D + dim] != 0 : true;
+}
+
+// Which specialised structure (if any) the base kernel has.
+//   1: one RBF over all dims, every plane shares it            (planar layout, or colour layout with C == 1)
+//   2: colour-patch layout with one RBF per channel (dims c::C) (cifar.py:33-41 "addwconv")
+//   0: anything else -> generic kernels
+static int fast_mode(const cgp_kernel_desc* d, const Geo& g) {
+  if (d->ard) return 0;
+  const bool size_ok = (d->ph == 5 && d->pw == 5) || (d->ph == 3 && d->pw == 3) || (d->ph == 2 && d->pw == 2);
+  if (!size_ok) return 0;
+  if (g.Hout < 1 || g.Wout < 1) return 0;
+  const bool planar = d->layout == CGP_LAYOUT_PLANAR || d->C == 1;
+  if (planar && d->n_groups == 1) {
+    for (int k = 0; k < g.D; ++k)
+      if (!mask_at(d, g.D, 0, k)) return 0;
+    return 1;
+  }
+  if (d->layout == CGP_LAYOUT_COLOUR_PATCH && d->n_groups == d->C && d->C > 1) {
+    for (int gi = 0; gi < d->C; ++gi)
+      for (int k = 0; k < g.D; ++k)
+        if (mask_at(d, g.D, gi, k) != ((k % d->C) == gi)) return 0;
+    return 2;
+  }
+  return 0;
+}
+
+template <typename T>
+static void fill_fast(FastParams<T>& p, const cgp_kernel_desc* d, const Geo& g, int mode, int N, int M) {
+  memset(&p, 0, sizeof(p));
+  p.N = N;
+  p.M = M;
+  p.H = d->H;
+  p.Wd = d->W;
+  p.C = d->C;
+  p.Hout = g.Hout;
+  p.Wout = g.Wout;
+  p.Pc = g.Pc;
+  p.Dtot = g.D;
+  if (mode == 2) {
+    p.zstride = d->C;
+    p.zplane = 1;
+    p.grp_per_plane = 1;
+    p.w_per_plane = 0;
+  } else {
+    p.zstride = 1;
+    p.zplane = 0;
+    p.grp_per_plane = 0;
+    p.w_per_plane = 1;  // Conv: weights are (C, P') channel-major; C == 1 makes this the plain case
+  }
+  p.out_per_channel = d->out_mode == CGP_OUT_PER_CHANNEL;
+  p.round_f32 = d->round_x_f32;
+  p.Pn = (double)g.P;
+}
+
+template <typename T>
+static size_t fast_smem(const FastParams<T>& p, int tpb, bool bwd) {
+  size_t nW = p.w_per_plane ? (size_t)p.C * p.Pc : (size_t)p.Pc;
+  size_t n = (size_t)p.C * p.H * p.Wd + (size_t)p.C * p.Pc + nW;
+  if (bwd) n += nW + (size_t)(tpb / 32) * 32 * (p.Wout | 1);
+  n += 32;  // block_sum scratch
+  return n * sizeof(T);
+}
+
+// pick warps-per-CTA in [lo, hi] that wastes the fewest lanes for `units` thread slots
+static int pick_warps(int units, int lo, int hi) {
+  int nw = (units + 31) / 32, best = lo, best_waste = 1 << 30;
+  for (int w = lo; w <= hi; ++w) {
+    int waste = ((nw + w - 1) / w) * w - nw;
+    if (waste < best_waste || (waste == best_waste && w > best)) {
+      best = w;
+      best_waste = waste;
+    }
+  }
+  return best;
+}
+
+template <typename K, typename P>
+static int launch_fast(K kernel, P& p, int tpb, size_t smem, cudaStream_t st, const char* name,
+                       long long min_items_per_cta = 1) {
+  if (smem > 227 * 1024) {
+    set_error("%s: needs %zu bytes of shared memory", name, smem);
+    return CGP_ERR_UNSUPPORTED;
+  }
+  CGP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CGP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, tpb, smem));
+  if (occ < 1) {
+    set_error("%s: zero occupancy (tpb=%d smem=%zu)", name, tpb, smem);
+    return CGP_ERR_UNSUPPORTED;
+  }
+  long long grid = std::min<long long>(p.n_items / min_items_per_cta, (long long)occ * num_sms());
+  if (p.n_items < 1) return CGP_OK;
+  if (grid < 1) grid = 1;
+  p.tpb = tpb;
+  kernel<<<(unsigned)grid, tpb, smem, st>>>(p);
+  CGP_CUDA_CHECK(cudaGetLastError());
+  return CGP_OK;
+}
+
+#define CGP_DISPATCH_PATCH(ph, pw, CALL)                \
+  if (ph == 5 && pw == 5) { CALL(5, 5); }               \
+  else if (ph == 3 && pw == 3) { CALL(3, 3); }          \
+  else if (ph == 2 && pw == 2) { CALL(2, 2); }          \
+  else { set_error("no specialised kernel for %dx%d patches", ph, pw); return CGP_ERR_UNSUPPORTED; }
+
+template <typename T, bool BWD>
+static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N, int M, const void* X,
+                        const void* Z, const void* W, const void* var, const void* ls, const void* G, void* out,
+                        void* dZ, void* dW, void* dvar, void* dls, cudaStream_t st) {
+  FastParams<T> p;
+  fill_fast(p, d, g, mode, N, M);
+  p.X = (const T*)X; p.Z = (const T*)Z; p.Wt = (const T*)W; p.var = (const T*)var; p.ls = (const T*)ls;
+  p.G = (const T*)G; p.out = (T*)out; p.dZ = (T*)dZ; p.dW = (T*)dW; p.dvar = (T*)dvar; p.dls = (T*)dls;
+  const int tpb = 32 * pick_warps(M, 1, 4);
+  const int nchunk = (M + tpb - 1) / tpb;
+  p.n_items = (long long)nchunk * N * d->C * g.Hout;
+  const size_t smem = fast_smem(p, tpb, BWD);
+  if (!BWD) {
+    size_t bytes = sizeof(T) * (size_t)M * N * (p.out_per_channel ? d->C : 1);
+    CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
+  }
+  // Every CTA walks at least one whole (chunk, image) unit's worth of rows, so an output element
+  // receives at most two atomic contributions -> the forward result is order-independent (the
+  // reference's tests demand bitwise equalities between kernels, testing/test_convkerns.py:112-128).
+  const long long unit = (long long)d->C * g.Hout;
+#define CALL(PH_, PW_) return launch_fast(kuf_fast_kernel<T, PH_, PW_, BWD>, p, tpb, smem, st, "kuf", unit)
+  CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+}
+
+template <typename T, bool BWD>
+static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N, const void* X, const void* W,
+                          const void* var, const void* ls, const void* G, void* out, void* dW, void* dvar,
+                          void* dls, cudaStream_t st) {
+  FastParams<T> p;
+  fill_fast(p, d, g, mode, N, 0);
+  p.X = (const T*)X; p.Wt = (const T*)W; p.var = (const T*)var; p.ls = (const T*)ls;
+  p.G = (const T*)G; p.out = (T*)out; p.dW = (T*)dW; p.dvar = (T*)dvar; p.dls = (T*)dls;
+  // pairing domains: per plane when each plane has its own output slot / RBF group, else all
+  // C*P' patches of the image pair with each other (Conv with colour_channels > 1)
+  p.ndom = (mode == 2 || p.out_per_channel) ? d->C : 1;
+  const int ppd = d->C / p.ndom, Pd = ppd * g.Pc, Hd = ppd * g.Hout;
+  const int tpb = 32 * pick_warps(Pd, 3, 8);
+  const int nchunk = (Pd + tpb - 1) / tpb;
+  const int maxspan = (31 + g.Wout - 1) / g.Wout;
+  p.S = std::min(Hd, Hd / 2 + 1 + maxspan);
+  p.n_items = (long long)N * p.ndom * nchunk * p.S;
+  const size_t smem = fast_smem(p, tpb, BWD);
+  if (!BWD) {
+    size_t bytes = sizeof(T) * (size_t)N * (p.out_per_channel ? d->C : 1);
+    CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
+  }
+#define CALL(PH_, PW_) return launch_fast(kdiag_fast_kernel<T, PH_, PW_, BWD>, p, tpb, smem, st, "kdiag")
+  CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+}
+
+static int need(const void* ptr, const char* name) {
+  if (!ptr) {
+    set_error("%s must not be NULL", name);
+    return CGP_ERR_BAD_POINTER;
+  }
+  if (((uintptr_t)ptr & 7u) != 0) {
+    set_error("%s is not 8-byte aligned", name);
+    return CGP_ERR_BAD_POINTER;
+  }
+  return CGP_OK;
+}
+
+}  // namespace cgp
+
+using namespace cgp;
+
+#define CGP_NEED(ptr)                            \
+  do {                                           \
+    int _s = need(ptr, #ptr);                    \
+    if (_s != CGP_OK) return _s;                 \
+  } while (0)
+#define CGP_TRY(expr)                            \
+  do {                                           \
+    int _s = (expr);                             \
+    if (_s != CGP_OK) return _s;                 \
+  } while (0)
+
+extern "C" {
+
+int cgp_version(void) { return CGP_VERSION; }
+
+const char* cgp_last_error(void) { return g_err; }
+
+const char* cgp_status_string(int s) {
+  switch (s) {
+    case CGP_OK: return "ok";
+    case CGP_ERR_BAD_DESC: return "bad descriptor";
+    case CGP_ERR_UNSUPPORTED: return "unsupported configuration";
+    case CGP_ERR_BAD_POINTER: return "bad pointer";
+    case CGP_ERR_CUDA: return "CUDA error";
+    case CGP_ERR_WORKSPACE: return "workspace too small";
+    case CGP_ERR_NOT_PD: return "matrix not positive definite";
+    case CGP_ERR_NCCL: return "NCCL error";
+    default: return "unknown status";
+  }
+}
+
+int cgp_geometry(const cgp_kernel_desc* d, int32_t* num_patches, int32_t* patch_len) {
+  Geo g;
+  CGP_TRY(geometry(d, &g));
+  if (num_patches) *num_patches = g.P;
+  if (patch_len) *patch_len = g.D;
+  return CGP_OK;
+}
+
+size_t cgp_workspace_bytes(const cgp_kernel_desc* d, int32_t N, int32_t M) {
+  Geo g;
+  if (geometry(d, &g) != CGP_OK) return 0;
+  if (fast_mode(d, g) != 0) return 0;
+  return generic_workspace_bytes(d, g.P, g.D, N, M);
+}
+
+int cgp_patches(const cgp_kernel_desc* d, int32_t N, const void* X, void* out, void* stream) {
+  Geo g;
+  CGP_TRY(geometry(d, &g));
+  if (N <= 0) return CGP_OK;
+  CGP_NEED(X);
+  CGP_NEED(out);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == CGP_F64) return launch_patches<double>(d, g.Pc, g.D, N, (const double*)X, (double*)out, st);
+  return launch_patches<float>(d, g.Pc, g.D, N, (const float*)X, (float*)out, st);
+}
+
+int cgp_kuf_fwd(const cgp_kernel_desc* d, int32_t N, int32_t M, const void* X, const void* Z, const void* W,
+                const void* variance, const void* lengthscales, void* Kuf, void* ws, size_t ws_bytes,
+                void* stream) {
+  Geo g;
+  CGP_TRY(geometry(d, &g));
+  if (N < 0 || M < 0) { set_error("negative N or M"); return CGP_ERR_BAD_DESC; }
+  if (N == 0 || M == 0) return CGP_OK;
+  CGP_NEED(X); CGP_NEED(Z); CGP_NEED(variance); CGP_NEED(lengthscales); CGP_NEED(Kuf);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mode = fast_mode(d, g);
+  if (mode) {
+    if (d->dtype == CGP_F64)
+      return run_kuf_fast<double, false>(d, g, mode, N, M, X, Z, W, variance, lengthscales, nullptr, Kuf, nullptr,
+                                         nullptr, nullptr, nullptr, st);
+    return run_kuf_fast<float, false>(d, g, mode, N, M, X, Z, W, variance, lengthscales, nullptr, Kuf, nullptr,
+                                      nullptr, nullptr, nullptr, st);
+  }
+  return generic_kuf(d, g.P, g.D, N, M, X, Z, W, variance, lengthscales, nullptr, Kuf, nullptr, nullptr, nullptr,
+                     nullptr, ws, ws_bytes, st);
+}
+
+int cgp_kuf_bwd(const cgp_kernel_desc* d, int32_t N, int32_t M, const void* X, const void* Z, const void* W,
+                const void* variance, const void* lengthscales, const void* G, void* dZ, void* dW,
+                void* dvariance, void* dlengthscales, void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  CGP_TRY(geometry(d, &g));
+  if (N < 0 || M < 0) { set_error("negative N or M"); return CGP_ERR_BAD_DESC; }
+  if (N == 0 || M == 0) return CGP_OK;
+  CGP_NEED(X); CGP_NEED(Z); CGP_NEED(variance); CGP_NEED(lengthscales); CGP_NEED(G);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mode = fast_mode(d, g);
+  if (mode) {
+    if (d->dtype == CGP_F64)
+      return run_kuf_fast<double, true>(d, g, mode, N, M, X, Z, W, variance, lengthscales, G, nullptr, dZ, dW,
+                                        dvariance, dlengthscales, st);
+    return run_kuf_fast<float, true>(d, g, mode, N, M, X, Z, W, variance, lengthscales, G, nullptr, dZ, dW,
+                                     dvariance, dlengthscales, st);
+  }
+  return generic_kuf(d, g.P, g.D, N, M, X, Z, W, variance, lengthscales, G, nullptr, dZ, dW, dvariance,
+                     dlengthscales, ws, ws_bytes, st);
+}
+
+int cgp_kdiag_fwd(const cgp_kernel_desc* d, int32_t N, const void* X, const void* W, const void* variance,
+                  const void* lengthscales, void* Kdiag, void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  CGP_TRY(geometry(d, &g));
+  if (N < 0) { set_error("negative N"); return CGP_ERR_BAD_DESC; }
+  if (N == 0) return CGP_OK;
+  CGP_NEED(X); CGP_NEED(variance); CGP_NEED(lengthscales); CGP_NEED(Kdiag);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mode = fast_mode(d, g);
+  if (mode) {
+    if (d->dtype == CGP_F64)
+      return run_kdiag_fast<double, false>(d, g, mode, N, X, W, variance, lengthscales, nullptr, Kdiag, nullptr,
+                                           nullptr, nullptr, st);
+    return run_kdiag_fast<float, false>(d, g, mode, N, X, W, variance, lengthscales, nullptr, Kdiag, nullptr,
+                                        nullptr, nullptr, st);
+  }
+  return generic_kxx(d, g.P, g.D, N, 0, X, nullptr, W, variance, lengthscales, nullptr, Kdiag, nullptr, nullptr,
+                     nullptr, /*diag_only=*/true, ws, ws_bytes, st);
+}
+
+int cgp_kdiag_bwd(const cgp_kernel_desc* d, int32_t N, const void* X, const void* W, const void* variance,
+                  const void* lengthscales, const void* gK, void* dW, void* dvariance, void* dlengthscales,
+                  void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  CGP_TRY(geometry(d, &g));
+  if (N < 0) { set_error("negative N"); return CGP_ERR_BAD_DESC; }
+  if (N == 0) return CGP_OK;
+  CGP_NEED(X); CGP_NEED(variance); CGP_NEED(lengthscales); CGP_NEED(gK);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mode = fast_mode(d, g);
+  if (mode) {
+    if (d->dtype == CGP_F64)
+      return run_kdiag_fast<double, true>(d, g, mode, N, X, W, variance, lengthscales, gK, nullptr, dW, dvariance,
+                                          dlengthscales, st);
+    return run_kdiag_fast<float, true>(d, g, mode, N, X, W, variance, lengthscales, gK, nullptr, dW, dvariance,
+                                       dlengthscales, st);
+  }
+  return generic_kxx(d, g.P, g.D, N, 0, X, nullptr, W, variance, lengthscales, gK, nullptr, dW, dvariance,
+                     dlengthscales, /*diag_only=*/true, ws, ws_bytes, st);
+}
+
+int cgp_kuu_fwd(const cgp_kernel_desc* d, int32_t M, const void* Z, const void* variance,
+                const void* lengthscales, double diag_add, void* Kuu, void* stream) {
+  Geo g;
+  CGP_TRY(geometry(d, &g));
+  if (M < 0) { set_error("negative M"); return CGP_ERR_BAD_DESC; }
+  if (M == 0) return CGP_OK;
+  CGP_NEED(Z); CGP_NEED(variance); CGP_NEED(lengthscales); CGP_NEED(Kuu);
+  return generic_kuu(d, g.D, M, Z, variance, lengthscales, diag_add, nullptr, Kuu, nullptr, nullptr, nullptr,
+                     (cudaStream_t)stream);
+}
+
+int cgp_kuu_bwd(const cgp_kernel_desc* d, int32_t M, const void* Z, const void* variance,
+                const void* lengthscales, const void* Gu, void* dZ, void* dvariance, void* dlengthscales,
+                void* stream) {
+  Geo g;
+  CGP_TRY(geometry(d, &g));
+  if (M < 0) { set_error("negative M"); return CGP_ERR_BAD_DESC; }
+  if (M == 0) return CGP_OK;
+  CGP_NEED(Z); CGP_NEED(variance); CGP_NEED(lengthscales); CGP_NEED(Gu);
+  return generic_kuu(d, g.D, M, Z, variance, lengthscales, 0.0, Gu, nullptr, dZ, dvariance, dlengthscales,
+                     (cudaStream_t)stream);
+}
+
+int cgp_kfull_fwd(const cgp_kernel_desc* d, int32_t N, int32_t N2, const void* X, const void* X2, const void* W,
+                  const void* variance, const void* lengthscales, void* K, void* ws, size_t ws_bytes,
+                  void* stream) {
+  Geo g;
+  CGP_TRY(geometry(d, &g));
+  if (N < 0 || N2 < 0) { set_error("negative N"); return CGP_ERR_BAD_DESC; }
+  if (X2 == nullptr) N2 = N;
+  if (N == 0 || N2 == 0) return CGP_OK;
+  CGP_NEED(X); CGP_NEED(variance); CGP_NEED(lengthscales); CGP_NEED(K);
+  if (d->out_mode == CGP_OUT_PER_CHANNEL && X2 != nullptr) {
+    set_error("K(X, X2) is not defined for per-channel weights (misvgp.py:37-38)");
+    return CGP_ERR_UNSUPPORTED;
+  }
+  return generic_kxx(d, g.P, g.D, N, N2, X, X2, W, variance, lengthscales, nullptr, K, nullptr, nullptr, nullptr,
+                     /*diag_only=*/false, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

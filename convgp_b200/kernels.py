@@ -1,0 +1,151 @@
+"""Base kernels with the GPflow 0.x surface the reference composes its patch kernels from
+(``GPflow.kernels.RBF / White / Add``; not in the reference tree -- semantics restated, see
+oracle/convgp_oracle.py header).  The patch-level evaluation of RBF members happens inside the
+CUDA library; ``RBF.K`` on whole inputs (the ``k2 = RBF(784)`` of sumkern_mnist.py:38-39) is a
+plain library GEMM."""
+import numpy as np
+import torch
+
+from .param import Param, Parameterized, Positive
+from .settings import settings
+
+
+def as_tensor(x, dtype=None):
+    """NumPy / torch in -> contiguous tensor of the float type on the compute device."""
+    dtype = dtype or settings.float_type
+    if isinstance(x, torch.Tensor):
+        return x.to(device=settings.device, dtype=dtype)
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float64)), dtype=dtype,
+                           device=settings.device)
+
+
+class Kern(Parameterized):
+    def __init__(self, input_dim, active_dims=None):
+        self.input_dim = int(input_dim)
+        self.active_dims = active_dims
+
+    def __add__(self, other):
+        return Add([self, other])
+
+    # inter-domain defaults of the GPflow fork: Kzx = K(Z, X), Kzz = K(Z)
+    def Kzx(self, Z, X):
+        return self.K(Z, X)
+
+    def Kzz(self, Z):
+        return self.K(Z)
+
+    # eager NumPy-in / NumPy-out twins (GPflow AutoFlow wrappers, testing/test_convkerns.py:54,118)
+    def compute_K_symm(self, X):
+        return self.K(as_tensor(X)).detach().cpu().numpy()
+
+    def compute_K(self, X, X2):
+        return self.K(as_tensor(X), as_tensor(X2)).detach().cpu().numpy()
+
+    def compute_Kdiag(self, X):
+        return self.Kdiag(as_tensor(X)).detach().cpu().numpy()
+
+    def compute_Kzz(self, Z):
+        return self.Kzz(as_tensor(Z)).detach().cpu().numpy()
+
+    def compute_Kzx(self, Z, X):
+        return self.Kzx(as_tensor(Z), as_tensor(X)).detach().cpu().numpy()
+
+
+class RBF(Kern):
+    """variance * exp(-|x - x'|^2 / (2 l^2)) on ``active_dims``; ``ARD`` gives one l per dim."""
+
+    def __init__(self, input_dim, variance=1.0, lengthscales=None, active_dims=None, ARD=False):
+        Kern.__init__(self, input_dim, active_dims)
+        self.ARD = bool(ARD)
+        self.variance = Param(np.asarray(variance, dtype=np.float64).reshape(-1)[:1].reshape(()), Positive())
+        if lengthscales is None:
+            lengthscales = np.ones(self.input_dim) if ARD else 1.0
+        ls = np.asarray(lengthscales, dtype=np.float64)
+        if ARD and ls.ndim == 0:
+            ls = ls * np.ones(self.input_dim)
+        self.lengthscales = Param(ls if ARD else ls.reshape(()), Positive())
+
+    def dims(self, D):
+        """Indices of the active dims inside a D-vector."""
+        ad = self.active_dims
+        if ad is None:
+            ad = slice(self.input_dim)
+        return np.arange(D)[ad]
+
+    def _slice(self, X):
+        idx = torch.as_tensor(self.dims(X.shape[1]), device=X.device)
+        return X if idx.numel() == X.shape[1] else X[:, idx]
+
+    def K(self, X, X2=None):
+        X = self._slice(X) / self.lengthscales()
+        Xs = (X * X).sum(1)
+        if X2 is None:
+            d = -2.0 * (X @ X.T) + Xs[:, None] + Xs[None, :]
+        else:
+            X2 = self._slice(X2) / self.lengthscales()
+            d = -2.0 * (X @ X2.T) + Xs[:, None] + (X2 * X2).sum(1)[None, :]
+        return self.variance() * torch.exp(-d / 2.0)
+
+    def Kdiag(self, X):
+        return self.variance() * torch.ones(X.shape[0], dtype=X.dtype, device=X.device)
+
+
+class White(Kern):
+    def __init__(self, input_dim, variance=1.0, active_dims=None):
+        Kern.__init__(self, input_dim, active_dims)
+        self.variance = Param(np.asarray(variance, dtype=np.float64).reshape(()), Positive())
+
+    def K(self, X, X2=None):
+        if X2 is None:
+            return self.variance() * torch.eye(X.shape[0], dtype=X.dtype, device=X.device)
+        return torch.zeros(X.shape[0], X2.shape[0], dtype=X.dtype, device=X.device)
+
+    def Kdiag(self, X):
+        return self.variance() * torch.ones(X.shape[0], dtype=X.dtype, device=X.device)
+
+
+class Add(Kern):
+    """Sum of kernels.  Members are reachable as ``kern_list[i]`` (mnist.py:47) and by GPflow's
+    auto-names: lower-cased class name, ``_1, _2, ...`` when repeated (sumkern_mnist.py:46-50)."""
+
+    def __init__(self, kern_list):
+        flat = []
+        for k in kern_list:
+            flat.extend(k.kern_list if isinstance(k, Add) else [k])
+        Kern.__init__(self, max(k.input_dim for k in flat))
+        self.kern_list = flat
+        names = [type(k).__name__.lower() for k in flat]
+        counts = {}
+        for k, nm in zip(flat, names):
+            if names.count(nm) > 1:
+                counts[nm] = counts.get(nm, 0) + 1
+                nm = "%s_%d" % (nm, counts[nm])
+            object.__setattr__(self, nm, k)
+
+    def _children(self):
+        for i, k in enumerate(self.kern_list):
+            yield "kern_list[%d]" % i, k
+
+    def K(self, X, X2=None):
+        return sum(k.K(X, X2) for k in self.kern_list)
+
+    def Kdiag(self, X):
+        return sum(k.Kdiag(X) for k in self.kern_list)
+
+    def Kzx(self, Z, X):
+        out = None
+        for k in self.kern_list:
+            if isinstance(k, White):
+                continue  # White.K(Z, X) == 0
+            v = k.Kzx(Z, X)
+            out = v if out is None else out + v
+        if out is None:
+            out = torch.zeros(Z.shape[0], X.shape[0], dtype=X.dtype, device=X.device)
+        return out
+
+    def Kzz(self, Z):
+        return sum(k.Kzz(Z) for k in self.kern_list)
+
+    @property
+    def inducing_outputs(self):
+        return max(getattr(k, "inducing_outputs", 1) for k in self.kern_list)

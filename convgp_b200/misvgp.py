@@ -1,0 +1,58 @@
+"""Multi-channel weighted conv kernel and the inter-domain conditional that consumes pre-evaluated
+kernel matrices (convgp/misvgp.py)."""
+import numpy as np
+import torch
+
+from . import _lib
+from .convkernels import Conv
+from .param import Param
+
+
+class WeightedMultiChannelConvGP(Conv):
+    """Per-channel patch weights ``W (C, P')`` and ``C`` inducing outputs per inducing patch
+    (misvgp.py:27-80): ``Kzx -> (M, N, C)``, ``Kdiag -> (N, C)``; ``K`` sums the channels."""
+
+    _out_mode = _lib.OUT_PER_CHANNEL
+
+    def __init__(self, basekern, img_size, patch_size, colour_channels=1):
+        Conv.__init__(self, basekern, img_size, patch_size, colour_channels)
+        self.basekern.input_dim = int(np.prod(patch_size))
+        self.W = Param(np.ones((self.colour_channels, self.num_patches // self.colour_channels)))
+
+    def _weights(self, dtype):
+        return self.W().to(dtype)
+
+    def K(self, X, X2=None):  # misvgp.py:33-49
+        if X2 is not None:
+            raise NotImplementedError
+        return Conv.K(self, X, None)
+
+    @property
+    def inducing_outputs(self):  # misvgp.py:75-80
+        return self.colour_channels
+
+
+def conditional(Xnew, X, Kdiag, Kmn, Kmm, f, full_cov=False, q_sqrt=None, whiten=False):
+    """misvgp.py:83-165: GP conditional from evaluated ``Kdiag (N)``, ``Kmn (M, N)``, ``Kmm (M, M)``.
+    Returns ``fmean (N, L)``, ``fvar (N, L)``.  ``Xnew`` / ``X`` are kept for signature parity only."""
+    if full_cov:
+        raise NotImplementedError("full_cov needs K(Xnew, Xnew), which this entry point is not given "
+                                  "(the reference's own branch is `None - A^T A`, misvgp.py:135)")
+    num_func = f.shape[1]
+    Lm = torch.linalg.cholesky(Kmm)  # :128
+    A = torch.linalg.solve_triangular(Lm, Kmn, upper=False)  # :131
+    fvar = Kdiag - (A * A).sum(0)  # :138
+    fvar = fvar[None, :].expand(num_func, -1)  # :140
+    if not whiten:  # :143-144
+        A = torch.linalg.solve_triangular(Lm.T, A, upper=True)
+    fmean = A.T @ f  # :147
+    if q_sqrt is not None:
+        if q_sqrt.dim() == 2:  # :150-151
+            LTA = A[None, :, :] * q_sqrt.T[:, :, None]
+        elif q_sqrt.dim() == 3:  # :152-155
+            Lq = torch.tril(q_sqrt.permute(2, 0, 1))
+            LTA = Lq.transpose(1, 2) @ A[None, :, :]
+        else:
+            raise ValueError("Bad dimension for q_sqrt: %s" % str(q_sqrt.dim()))
+        fvar = fvar + (LTA * LTA).sum(1)  # :162
+    return fmean, fvar.T  # :163-165

@@ -1,0 +1,148 @@
+"""torch.autograd wrappers around the C ABI: the only place PyTorch meets the CUDA library.
+PyTorch is the tensor carrier (device memory, streams, autograd tape); all arithmetic of the hot
+path happens in libconvgp_b200.so.  Gradients follow SURVEY.md section 8a."""
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def _c(t):
+    if t is not None and not t.is_cuda:
+        raise _lib.CgpError(-3, "tensor is not on a CUDA device (convgp_b200 has no CPU path)")
+    return None if t is None else t.contiguous()
+
+
+def _grad_buffers(spec, Z, W, variance, lengthscales):
+    """One zeroed, packed gradient buffer [dZ | dW | dvariance | dlengthscales] and its views.
+    The C ABI accumulates into it, and it is what the data-parallel all-reduce sums."""
+    sizes = [0 if Z is None else Z.numel(), 0 if W is None else W.numel(), variance.numel(), lengthscales.numel()]
+    buf = torch.zeros(sum(sizes), dtype=variance.dtype, device=variance.device)
+    views, o = [], 0
+    for s, ref in zip(sizes, (Z, W, variance, lengthscales)):
+        views.append(None if ref is None else buf[o:o + s].view(ref.shape))
+        o += s
+    return buf, views
+
+
+class _Kuf(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, X, Z, W, variance, lengthscales):
+        X, Z, W, variance, lengthscales = map(_c, (X, Z, W, variance, lengthscales))
+        N, M = X.shape[0], Z.shape[0]
+        shape = (M, N, spec.C) if spec.per_channel else (M, N)
+        out = torch.empty(shape, dtype=X.dtype, device=X.device)
+        with torch.cuda.device(X.device):
+            ws, nb = spec.workspace(N, M, X.device)
+            check(_lib.lib().cgp_kuf_fwd(spec.ref(), N, M, ptr(X), ptr(Z), ptr(W), ptr(variance), ptr(lengthscales),
+                                         ptr(out), ptr(ws), nb, stream_ptr()))
+        ctx.spec = spec
+        ctx.save_for_backward(X, Z, W, variance, lengthscales)
+        return out
+
+    @staticmethod
+    def backward(ctx, G):
+        X, Z, W, variance, lengthscales = ctx.saved_tensors
+        spec = ctx.spec
+        N, M = X.shape[0], Z.shape[0]
+        _, (dZ, dW, dvar, dls) = _grad_buffers(spec, Z, W, variance, lengthscales)
+        G = G.contiguous()
+        with torch.cuda.device(X.device):
+            ws, nb = spec.workspace(N, M, X.device)
+            check(_lib.lib().cgp_kuf_bwd(spec.ref(), N, M, ptr(X), ptr(Z), ptr(W), ptr(variance), ptr(lengthscales),
+                                         ptr(G), ptr(dZ), ptr(dW), ptr(dvar), ptr(dls), ptr(ws), nb, stream_ptr()))
+        return None, None, dZ, dW, dvar, dls
+
+
+class _Kdiag(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, X, W, variance, lengthscales):
+        X, W, variance, lengthscales = map(_c, (X, W, variance, lengthscales))
+        N = X.shape[0]
+        shape = (N, spec.C) if spec.per_channel else (N,)
+        out = torch.empty(shape, dtype=X.dtype, device=X.device)
+        with torch.cuda.device(X.device):
+            ws, nb = spec.workspace(N, 0, X.device)
+            check(_lib.lib().cgp_kdiag_fwd(spec.ref(), N, ptr(X), ptr(W), ptr(variance), ptr(lengthscales), ptr(out),
+                                           ptr(ws), nb, stream_ptr()))
+        ctx.spec = spec
+        ctx.save_for_backward(X, W, variance, lengthscales)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        X, W, variance, lengthscales = ctx.saved_tensors
+        spec = ctx.spec
+        N = X.shape[0]
+        _, (_, dW, dvar, dls) = _grad_buffers(spec, None, W, variance, lengthscales)
+        g = g.contiguous()
+        with torch.cuda.device(X.device):
+            ws, nb = spec.workspace(N, 0, X.device)
+            check(_lib.lib().cgp_kdiag_bwd(spec.ref(), N, ptr(X), ptr(W), ptr(variance), ptr(lengthscales), ptr(g),
+                                           ptr(dW), ptr(dvar), ptr(dls), ptr(ws), nb, stream_ptr()))
+        return None, None, dW, dvar, dls
+
+
+class _Kuu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, Z, variance, lengthscales, diag_add):
+        Z, variance, lengthscales = map(_c, (Z, variance, lengthscales))
+        M = Z.shape[0]
+        out = torch.empty((M, M), dtype=Z.dtype, device=Z.device)
+        with torch.cuda.device(Z.device):
+            check(_lib.lib().cgp_kuu_fwd(spec.ref(), M, ptr(Z), ptr(variance), ptr(lengthscales), float(diag_add),
+                                         ptr(out), stream_ptr()))
+        ctx.spec = spec
+        ctx.save_for_backward(Z, variance, lengthscales)
+        return out
+
+    @staticmethod
+    def backward(ctx, Gu):
+        Z, variance, lengthscales = ctx.saved_tensors
+        spec = ctx.spec
+        M = Z.shape[0]
+        _, (dZ, _, dvar, dls) = _grad_buffers(spec, Z, None, variance, lengthscales)
+        Gu = Gu.contiguous()
+        with torch.cuda.device(Z.device):
+            check(_lib.lib().cgp_kuu_bwd(spec.ref(), M, ptr(Z), ptr(variance), ptr(lengthscales), ptr(Gu), ptr(dZ),
+                                         ptr(dvar), ptr(dls), stream_ptr()))
+        return None, dZ, dvar, dls, None
+
+
+def kuf(spec, X, Z, W, variance, lengthscales):
+    """Kzx(Z, X): (M, N) or (M, N, C)."""
+    return _Kuf.apply(spec, X, Z, W, variance, lengthscales)
+
+
+def kdiag(spec, X, W, variance, lengthscales):
+    """Kdiag(X): (N,) or (N, C)."""
+    return _Kdiag.apply(spec, X, W, variance, lengthscales)
+
+
+def kuu(spec, Z, variance, lengthscales, diag_add=0.0):
+    """Kzz(Z) + diag_add * I."""
+    return _Kuu.apply(spec, Z, variance, lengthscales, diag_add)
+
+
+def kfull(spec, X, X2, W, variance, lengthscales):
+    """K(X, X2) (forward only: the reference uses it in tests and full-GP baselines, never inside
+    the SVGP objective)."""
+    X, X2, W, variance, lengthscales = map(_c, (X, X2, W, variance, lengthscales))
+    N = X.shape[0]
+    N2 = N if X2 is None else X2.shape[0]
+    out = torch.empty((N, N2), dtype=X.dtype, device=X.device)
+    with torch.cuda.device(X.device):
+        nb = (N + N2) * spec.P * spec.D * X.element_size() + 256  # materialised patches of X and X2
+        ws = torch.empty(nb, dtype=torch.uint8, device=X.device)
+        check(_lib.lib().cgp_kfull_fwd(spec.ref(), N, N2, ptr(X), ptr(X2), ptr(W), ptr(variance), ptr(lengthscales),
+                                       ptr(out), ptr(ws), nb, stream_ptr()))
+    return out
+
+
+def patches(spec, X):
+    """_get_patches(X): (N, P, D)."""
+    X = _c(X)
+    out = torch.empty((X.shape[0], spec.P, spec.D), dtype=X.dtype, device=X.device)
+    with torch.cuda.device(X.device):
+        check(_lib.lib().cgp_patches(spec.ref(), X.shape[0], ptr(X), ptr(out), stream_ptr()))
+    return out

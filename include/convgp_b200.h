@@ -1,0 +1,125 @@
+/* convgp_b200 -- C ABI of the B200-native patch-kernel hot path.
+ *
+ * Every entry point replaces a method of the reference's Python kernel classes (there is no
+ * native code and no FFI in /root/reference; the "interface each one replaces" is therefore
+ * the graph-building method a caller invokes, cited per function as file:line under
+ * /root/reference).  The boundary is plain C: POD descriptor, raw DEVICE pointers, sizes and a
+ * CUDA stream handle.  No torch / C++ types appear here.
+ *
+ * Conventions
+ *  - All tensors are contiguous row-major device buffers of the descriptor's dtype.
+ *    X: (N, H*W*C) pixel-major / channel-minor (convkernels.py:52-54, :136).
+ *    Z: (M, D).  Kuf: (M, N) or (M, N, C) for CGP_OUT_PER_CHANNEL.  Kdiag: (N) or (N, C).
+ *    W: (P) patch weights (channel-major, then row-major position; for per-channel output it
+ *       is the (C, P') matrix of misvgp.py:31) or NULL for the unweighted Conv kernel.
+ *  - The base kernel is a sum of n_groups RBF members (GPflow `RBF` / `Add`):
+ *       k(a,b) = sum_g variance[g] * exp(-0.5 * sum_{d in active(g)} (a_d-b_d)^2 / ls[g,d]^2)
+ *    variance: (n_groups).  lengthscales: (n_groups) if !ard, else (n_groups, D) (entries of
+ *    inactive dims are ignored).  `active` is a HOST byte mask (n_groups*D) or NULL (= all).
+ *  - Forward outputs are overwritten.  Backward outputs (dZ, dW, dvariance, dlengthscales) are
+ *    ACCUMULATED INTO (+=): the caller zeroes its packed gradient buffer once per step, which
+ *    is also the buffer the data-parallel all-reduce sums.  Any gradient
+ *    pointer may be NULL to skip it.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates
+ *    nothing persistent, and is safe under CUDA-graph capture.  Return value: 0 or a negative
+ *    cgp_status; cgp_last_error() gives the thread-local message.  Nothing ever aborts.
+ */
+#ifndef CONVGP_B200_H
+#define CONVGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGP_VERSION 100 /* 0.1.0 */
+
+enum cgp_dtype { CGP_F32 = 0, CGP_F64 = 1 };
+/* Conv._get_patches (convkernels.py:38-62): channels are separate images, D = ph*pw, P = C*P'.
+ * ColourPatchConv._get_patches (convkernels.py:128-141): D = ph*pw*C ordered (i,j,c), P = P'. */
+enum cgp_layout { CGP_LAYOUT_PLANAR = 0, CGP_LAYOUT_COLOUR_PATCH = 1 };
+/* CGP_OUT_PER_CHANNEL: WeightedMultiChannelConvGP (misvgp.py:51-73). */
+enum cgp_out_mode { CGP_OUT_SUM = 0, CGP_OUT_PER_CHANNEL = 1 };
+
+enum cgp_status {
+  CGP_OK = 0,
+  CGP_ERR_BAD_DESC = -1,    /* inconsistent shapes / enum out of range            */
+  CGP_ERR_UNSUPPORTED = -2, /* valid but no kernel for it (never a silent fallback) */
+  CGP_ERR_BAD_POINTER = -3, /* required pointer NULL or misaligned                 */
+  CGP_ERR_CUDA = -4,        /* CUDA runtime error (message in cgp_last_error)      */
+  CGP_ERR_WORKSPACE = -5,   /* workspace too small                                 */
+  CGP_ERR_NOT_PD = -6,      /* Cholesky pivot <= 0 (index via cgp_last_error)      */
+  CGP_ERR_NCCL = -7
+};
+
+typedef struct cgp_kernel_desc {
+  int32_t dtype;       /* cgp_dtype */
+  int32_t H, W, C;     /* image rows, cols, colour channels (img_size, colour_channels) */
+  int32_t ph, pw;      /* patch_size */
+  int32_t layout;      /* cgp_layout */
+  int32_t out_mode;    /* cgp_out_mode */
+  int32_t n_groups;    /* members of the additive RBF base kernel (>= 1) */
+  int32_t ard;         /* lengthscales is (n_groups, D) instead of (n_groups) */
+  int32_t round_x_f32; /* reproduce ColourPatchConv's float32 rounding of X (convkernels.py:134,141) */
+  int32_t reserved;
+  const uint8_t* active; /* HOST pointer: (n_groups, D) 0/1 mask, or NULL = every dim active */
+} cgp_kernel_desc;
+
+int cgp_version(void);
+const char* cgp_last_error(void);
+const char* cgp_status_string(int status);
+
+/* patch_len / num_patches properties (convkernels.py:105-112, :143-149). */
+int cgp_geometry(const cgp_kernel_desc* d, int32_t* num_patches, int32_t* patch_len);
+
+/* Scratch the generic (non-specialised) kernels need for N images / M inducing patches.
+ * The specialised kernels need none; callers may always pass what this returns. */
+size_t cgp_workspace_bytes(const cgp_kernel_desc* d, int32_t N, int32_t M);
+
+/* compute_patches / _get_patches (convkernels.py:38-62, :114-116, :128-141): out (N, P, D). */
+int cgp_patches(const cgp_kernel_desc* d, int32_t N, const void* X, void* out, void* stream);
+
+/* Kzx (convkernels.py:82-87 Conv, :183-190 WeightedConv, :211-248 ConvRBF variants;
+ * misvgp.py:66-73 per-channel). */
+int cgp_kuf_fwd(const cgp_kernel_desc* d, int32_t N, int32_t M, const void* X, const void* Z, const void* W,
+                const void* variance, const void* lengthscales, void* Kuf, void* ws, size_t ws_bytes,
+                void* stream);
+/* Reverse mode of the above (the reference relies on TF autodiff; closed forms: SURVEY.md 8a).
+ * G = dL/dKuf with Kuf's shape. */
+int cgp_kuf_bwd(const cgp_kernel_desc* d, int32_t N, int32_t M, const void* X, const void* Z, const void* W,
+                const void* variance, const void* lengthscales, const void* G, void* dZ, void* dW,
+                void* dvariance, void* dlengthscales, void* ws, size_t ws_bytes, void* stream);
+
+/* Kdiag (convkernels.py:73-79 Conv, :173-181 WeightedConv; misvgp.py:51-64 per-channel (N,C)). */
+int cgp_kdiag_fwd(const cgp_kernel_desc* d, int32_t N, const void* X, const void* W, const void* variance,
+                  const void* lengthscales, void* Kdiag, void* ws, size_t ws_bytes, void* stream);
+int cgp_kdiag_bwd(const cgp_kernel_desc* d, int32_t N, const void* X, const void* W, const void* variance,
+                  const void* lengthscales, const void* g, void* dW, void* dvariance, void* dlengthscales,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* Kzz (convkernels.py:89-90): basekern.K(Z); `diag_add` (jitter + White variance, svsumgp.py:76,
+ * misvgp.py:196) is added to the diagonal in the same pass. */
+int cgp_kuu_fwd(const cgp_kernel_desc* d, int32_t M, const void* Z, const void* variance,
+                const void* lengthscales, double diag_add, void* Kuu, void* stream);
+int cgp_kuu_bwd(const cgp_kernel_desc* d, int32_t M, const void* Z, const void* variance,
+                const void* lengthscales, const void* Gu, void* dZ, void* dvariance, void* dlengthscales,
+                void* stream);
+
+/* K(X, X2) (convkernels.py:64-71, :157-171; misvgp.py:33-49 for per-channel weights, X2 == NULL only):
+ * out (N, N2).  X2 == NULL means the symmetric K(X). */
+int cgp_kfull_fwd(const cgp_kernel_desc* d, int32_t N, int32_t N2, const void* X, const void* X2, const void* W,
+                  const void* variance, const void* lengthscales, void* K, void* ws, size_t ws_bytes,
+                  void* stream);
+
+/* Pipe-throughput probes used by bench.py for the compute roofline: runs a
+ * dependent-chain micro-kernel on the current device, synchronises, and returns operations per
+ * second in *ops_per_s.  kind: 0 = FP64 FMA, 1 = FP32 FMA, 2 = MUFU ex2.approx.f32,
+ * 3 = this library's double-precision exp, 4 = FP64 mma.sync m8n8k4 (counted as FMAs). */
+int cgp_peak_probe(int32_t kind, double* ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONVGP_B200_H */

@@ -1,0 +1,90 @@
+"""Parity of the CUDA path (through the package classes -> ctypes -> C ABI) against the NumPy oracle
+and the torch-twin gradients.  Tolerances are BASELINE.json's: 1e-10 (float64) and 1e-4 (float32),
+relative to max|.| of each array."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import Case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float64: 1e-10, torch.float32: 1e-4}
+
+S3 = np.s_
+
+
+def cases():
+    rbf = lambda v=1.0, l=1.0: [(v, l, None, False)]  # noqa: E731
+    return [
+        # --- specialised kernels (fast path)
+        Case("mnist5x5", "conv", 28, 28, 1, 5, 5, rbf(0.8, 1.7), N=5, M=40),
+        Case("mnist5x5_unweighted", "conv", 28, 28, 1, 5, 5, rbf(1.3, 0.9), weighted=False, N=3, M=33),
+        Case("rect3x3", "conv", 28, 28, 1, 3, 3, rbf(0.7, 2.1), weighted=False, N=4, M=16),
+        Case("tiny2x2", "conv", 3, 3, 1, 2, 2, rbf(), N=3, M=5, xdist="randn"),
+        Case("odd_rows", "conv", 9, 11, 1, 3, 3, rbf(1.1, 1.4), N=3, M=70),
+        Case("planar_c3", "conv", 12, 12, 3, 5, 5, rbf(0.9, 1.2), N=4, M=20),
+        Case("planar_c2_unw", "conv", 8, 8, 2, 3, 3, rbf(1.0, 0.8), weighted=False, N=3, M=9),
+        Case("multi_c3", "multi", 12, 12, 3, 5, 5, rbf(1.2, 1.1), N=4, M=20),
+        Case("cifar_addwconv", "colour", 12, 12, 3, 5, 5,
+             [(1.01, 0.5, S3[0::3], False), (0.99, 0.6, S3[1::3], False), (1.02, 0.7, S3[2::3], False)],
+             N=3, M=20, xdist="uint8"),
+        # --- generic kernels
+        Case("cpwconv", "colour", 10, 10, 3, 5, 5, rbf(1.1, 2.5), N=3, M=12, xdist="uint8"),
+        Case("patch4x4", "conv", 10, 10, 1, 4, 4, rbf(0.9, 1.5), N=3, M=10),
+        Case("ard3x3", "conv", 8, 8, 1, 3, 3, [(0.8, np.linspace(0.8, 1.6, 9), None, True)], N=3, M=10),
+        Case("wconv_add", "conv", 8, 8, 1, 3, 3,
+             [(1.0, 1.0, None, False), (0.5, 0.7, S3[0:3], False), (0.6, 0.9, S3[3:6], False),
+              (0.7, 1.1, S3[0:7:3], False), (0.4, np.array([0.9, 1.2, 1.5]), S3[2:9:3], True)], N=3, M=10),
+        Case("multi_generic", "multi", 9, 9, 2, 4, 4, rbf(1.2, 1.1), N=3, M=8),
+    ]
+
+
+CASES = cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_forward_and_backward_match_oracle(case, dtype):
+    tol = TOL[dtype]
+    ok = case.oracle_kernel()
+    ref = case.twin_grads()
+    # the twin is itself checked against the NumPy oracle here (values)
+    assert rel_err(ref["kuf"], ok.Kzx(case.Z, case.X)) < 1e-12
+    assert rel_err(ref["kdiag"], ok.Kdiag(case.X)) < 1e-12
+    got = case.package_grads(dtype)
+    for key in ("kuf", "kdiag", "kuu", "dZ"):
+        assert rel_err(got[key], ref[key]) < tol, key
+    if case.weighted:
+        assert rel_err(got["dW"], ref["dW"]) < tol, "dW"
+    # hyper-parameter gradients: compare as one vector so tiny members are judged relative to the largest
+    gv = np.concatenate([np.ravel(v) for v in got["dvar"]])
+    rv = np.concatenate([np.ravel(v) for v in ref["dvar"]])
+    gl = np.concatenate([np.ravel(v) for v in got["dls"]])
+    rl = np.concatenate([np.ravel(v) for v in ref["dls"]])
+    assert rel_err(gv, rv) < tol * 10, "dvariance"
+    assert rel_err(gl, rl) < tol * 10, "dlengthscales"
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c.kind != "multi"][:6] + [c for c in CASES if c.name in
+                                                                               ("cpwconv", "wconv_add")],
+                         ids=lambda c: c.name)
+def test_full_K_and_patches(case):
+    from convgp_b200.kernels import as_tensor
+    k, ok = case.package_kernel(), case.oracle_kernel()
+    X = as_tensor(case.X)
+    assert np.max(np.abs(k.compute_patches(case.X) - ok._get_patches(case.X))) == 0  # bit-exact im2col
+    assert rel_err(k.K(X).cpu().numpy(), ok.K(case.X)) < 1e-10
+    assert rel_err(k.K(X, X[:2]).cpu().numpy(), ok.K(case.X, case.X[:2])) < 1e-10
+    assert rel_err(np.diag(k.K(X).cpu().numpy()), k.Kdiag(X).detach().cpu().numpy()) < 1e-10
+
+
+def test_full_size_mnist_kuf_kdiag_f64():
+    """BASELINE config 3 at full size (28x28, 5x5, M=750, N=200), forward values vs the oracle."""
+    case = Case("cfg3", "conv", 28, 28, 1, 5, 5, [(1.0, 1.0, None, False)], N=200, M=750, seed=0)
+    from convgp_b200.kernels import as_tensor
+    k, ok = case.package_kernel(), case.oracle_kernel()
+    X, Z = as_tensor(case.X), as_tensor(case.Z)
+    assert rel_err(k.Kzx(Z, X).detach().cpu().numpy(), ok.Kzx(case.Z, case.X)) < 1e-10
+    assert rel_err(k.Kdiag(X).detach().cpu().numpy(), ok.Kdiag(case.X)) < 1e-10
+    assert rel_err(k.Kzz(Z).detach().cpu().numpy(), ok.Kzz(case.Z)) < 1e-10
