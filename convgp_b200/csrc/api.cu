@@ -3,9 +3,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <mutex>
+#include <tuple>
 
 #include "fast.cuh"
+#include "kuu_fast.cuh"
 #include "generic.cuh"
 
 namespace cgp {
@@ -164,6 +167,20 @@ static int pick_warps(int units, int lo, int hi) {
   return best;
 }
 
+// Occupancy per (kernel, threads, dynamic smem), per device: queried once, then launches are a plain
+// <<<>>> (cheap, and legal under stream capture).
+struct LaunchKey {
+  const void* fn;
+  int dev, tpb;
+  size_t smem;
+  bool operator<(const LaunchKey& o) const {
+    return std::tie(fn, dev, tpb, smem) < std::tie(o.fn, o.dev, o.tpb, o.smem);
+  }
+};
+static std::mutex g_launch_mu;
+static std::map<LaunchKey, int> g_launch_occ;
+static std::map<std::pair<const void*, int>, size_t> g_launch_smem;
+
 template <typename K, typename P>
 static int launch_fast(K kernel, P& p, int tpb, size_t smem, cudaStream_t st, const char* name,
                        long long min_items_per_cta = 1) {
@@ -171,15 +188,32 @@ static int launch_fast(K kernel, P& p, int tpb, size_t smem, cudaStream_t st, co
     set_error("%s: needs %zu bytes of shared memory", name, smem);
     return CGP_ERR_UNSUPPORTED;
   }
-  CGP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.n_items < 1) return CGP_OK;
+  int dev = 0;
+  CGP_CUDA_CHECK(cudaGetDevice(&dev));
   int occ = 0;
-  CGP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, tpb, smem));
+  {
+    std::lock_guard<std::mutex> lk(g_launch_mu);
+    LaunchKey key{(const void*)kernel, dev, tpb, smem};
+    auto it = g_launch_occ.find(key);
+    if (it == g_launch_occ.end()) {
+      // the opt-in shared-memory limit is per kernel (not per launch shape): only ever raise it
+      size_t& cur = g_launch_smem[std::make_pair((const void*)kernel, dev)];
+      if (smem > cur) {
+        CGP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+      }
+      CGP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, tpb, smem));
+      g_launch_occ[key] = occ;
+    } else {
+      occ = it->second;
+    }
+  }
   if (occ < 1) {
     set_error("%s: zero occupancy (tpb=%d smem=%zu)", name, tpb, smem);
     return CGP_ERR_UNSUPPORTED;
   }
   long long grid = std::min<long long>(p.n_items / min_items_per_cta, (long long)occ * num_sms());
-  if (p.n_items < 1) return CGP_OK;
   if (grid < 1) grid = 1;
   p.tpb = tpb;
   kernel<<<(unsigned)grid, tpb, smem, st>>>(p);
@@ -243,6 +277,36 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
 #define CALL(PH_, PW_) return launch_fast(kdiag_fast_kernel<T, PH_, PW_, BWD>, p, tpb, smem, st, "kdiag")
   CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL
+}
+
+template <typename T, bool BWD>
+static int run_kuu_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int M, const void* Z, const void* var,
+                        const void* ls, double diag_add, const void* Gu, void* out, void* dZ, void* dvar,
+                        void* dls, cudaStream_t st) {
+  KuuParams<T> p;
+  memset(&p, 0, sizeof(p));
+  p.Z = (const T*)Z; p.var = (const T*)var; p.ls = (const T*)ls; p.Gu = (const T*)Gu;
+  p.out = (T*)out; p.dZ = (T*)dZ; p.dvar = (T*)dvar; p.dls = (T*)dls;
+  p.M = M;
+  p.Dtot = g.D;
+  p.diag_add = diag_add;
+  if (mode == 2) { p.zstride = d->C; p.zplane = 1; p.nplanes = d->C; p.grp_per_plane = 1; }
+  else { p.zstride = 1; p.zplane = 0; p.nplanes = 1; p.grp_per_plane = 0; }
+  const int nic = (M + kKuuTPB - 1) / kKuuTPB;
+  const int njc_target = std::max(1, (2 * num_sms()) / nic);
+  int JT = (M + njc_target - 1) / njc_target;
+  JT = ((JT + kKuuJG - 1) / kKuuJG) * kKuuJG;
+  JT = std::max(JT, 4 * kKuuJG);
+  p.JT = JT;
+  const int njc = (M + JT - 1) / JT;
+  const int Dp = d->ph * d->pw;
+  const size_t smem = sizeof(T) * ((size_t)JT * Dp + JT);
+  dim3 grid(nic, njc);
+#define CALL(PH_, PW_) kuu_fast_kernel<T, PH_ * PW_, BWD><<<grid, kKuuTPB, smem, st>>>(p)
+  CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+  CGP_CUDA_CHECK(cudaGetLastError());
+  return CGP_OK;
 }
 
 static int need(const void* ptr, const char* name) {
@@ -408,6 +472,13 @@ int cgp_kuu_fwd(const cgp_kernel_desc* d, int32_t M, const void* Z, const void* 
   if (M < 0) { set_error("negative M"); return CGP_ERR_BAD_DESC; }
   if (M == 0) return CGP_OK;
   CGP_NEED(Z); CGP_NEED(variance); CGP_NEED(lengthscales); CGP_NEED(Kuu);
+  if (const int mode = fast_mode(d, g)) {
+    if (d->dtype == CGP_F64)
+      return run_kuu_fast<double, false>(d, g, mode, M, Z, variance, lengthscales, diag_add, nullptr, Kuu, nullptr,
+                                         nullptr, nullptr, (cudaStream_t)stream);
+    return run_kuu_fast<float, false>(d, g, mode, M, Z, variance, lengthscales, diag_add, nullptr, Kuu, nullptr,
+                                      nullptr, nullptr, (cudaStream_t)stream);
+  }
   return generic_kuu(d, g.D, M, Z, variance, lengthscales, diag_add, nullptr, Kuu, nullptr, nullptr, nullptr,
                      (cudaStream_t)stream);
 }
@@ -420,6 +491,13 @@ int cgp_kuu_bwd(const cgp_kernel_desc* d, int32_t M, const void* Z, const void* 
   if (M < 0) { set_error("negative M"); return CGP_ERR_BAD_DESC; }
   if (M == 0) return CGP_OK;
   CGP_NEED(Z); CGP_NEED(variance); CGP_NEED(lengthscales); CGP_NEED(Gu);
+  if (const int mode = fast_mode(d, g)) {
+    if (d->dtype == CGP_F64)
+      return run_kuu_fast<double, true>(d, g, mode, M, Z, variance, lengthscales, 0.0, Gu, nullptr, dZ, dvariance,
+                                        dlengthscales, (cudaStream_t)stream);
+    return run_kuu_fast<float, true>(d, g, mode, M, Z, variance, lengthscales, 0.0, Gu, nullptr, dZ, dvariance,
+                                     dlengthscales, (cudaStream_t)stream);
+  }
   return generic_kuu(d, g.D, M, Z, variance, lengthscales, 0.0, Gu, nullptr, dZ, dvariance, dlengthscales,
                      (cudaStream_t)stream);
 }

@@ -77,38 +77,64 @@ __device__ __forceinline__ void stage_image(const FastParams<T>& p, int n, T* im
   __syncthreads();
 }
 
-// Walk patch row r of one plane.  For every patch q the functor receives
-//   f(q, k, arg, xget)   k = exp(arg),  xget(i, j) = patch element (compile-time indices)
-template <typename T, int PH, int PW, class F>
-__device__ __forceinline__ void sweep_row(const T* __restrict__ plane, int Wd, int r, int Wout,
-                                          const T (&ref)[PH * PW], T e_ref, const T* __restrict__ erow, F&& f) {
-  T win[PH][PW];
-  const T* row0 = plane + r * Wd;
+// ---- patch-row sweep -------------------------------------------------------------------------
+// A warp walks a patch row in groups of PW consecutive patches.  Within a group the 2*PW-1 image
+// columns stream through PH registers each (warp-uniform shared-memory broadcasts) and every
+// column feeds all patches it belongs to, so the group is straight-line code with PW (x2)
+// independent FMA chains followed by PW independent exp evaluations: the FP64 pipe's dependent-
+// issue latency (~20 cycles measured) is covered by instruction-level parallelism instead of by
+// occupancy.  The last group of a row may contain patches q >= Wout: they read in-bounds
+// (initialised) shared memory just past the row and are masked with selects, never multiplied.
+
+// arg[u] = e_ref + erow[q0 + u] + dot(ref, patch(q0 + u)),  k[u] = exp(arg[u])
+template <typename T, int PH, int PW>
+__device__ __forceinline__ void group_eval(const T* __restrict__ col0, int Wd, const T (&ref)[PH * PW], T e_ref,
+                                           const T* __restrict__ erow_q0, T (&arg)[PW], T (&k)[PW]) {
+  T a1[PW];
 #pragma unroll
-  for (int j = 0; j < PW - 1; ++j)
+  for (int u = 0; u < PW; ++u) {
+    arg[u] = e_ref + erow_q0[u];
+    a1[u] = T(0);
+  }
 #pragma unroll
-    for (int i = 0; i < PH; ++i) win[i][j] = row0[i * Wd + j];
-  for (int q0 = 0; q0 < Wout; q0 += PW) {
+  for (int c = 0; c < 2 * PW - 1; ++c) {
+    T x[PH];
+#pragma unroll
+    for (int i = 0; i < PH; ++i) x[i] = col0[i * Wd + c];
 #pragma unroll
     for (int u = 0; u < PW; ++u) {
-      const int q = q0 + u;
-      if (q < Wout) {
+      const int j = c - u;
+      if (j >= 0 && j < PW) {
 #pragma unroll
-        for (int i = 0; i < PH; ++i) win[i][(u + PW - 1) % PW] = row0[i * Wd + q + PW - 1];
-        T a0 = e_ref + erow[q];
-        T a1 = T(0);
+        for (int i = 0; i < PH; ++i) {
+          if ((i & 1) == 0) arg[u] = fma_t(x[i], ref[i * PW + j], arg[u]);
+          else a1[u] = fma_t(x[i], ref[i * PW + j], a1[u]);
+        }
+      }
+    }
+  }
 #pragma unroll
-        for (int i = 0; i < PH; ++i)
+  for (int u = 0; u < PW; ++u) {
+    arg[u] += a1[u];
+    k[u] = Math<T>::exp_arg(arg[u]);
+  }
+}
+
+// acc[i*PW + j] += sum_u coef[u] * patch(q0 + u)[i][j]   (second pass over the same columns)
+template <typename T, int PH, int PW>
+__device__ __forceinline__ void group_accum(const T* __restrict__ col0, int Wd, const T (&coef)[PW],
+                                            T (&acc)[PH * PW]) {
 #pragma unroll
-          for (int j = 0; j < PW; ++j) {
-            if (((i * PW + j) & 1) == 0)
-              a0 = fma_t(win[i][(u + j) % PW], ref[i * PW + j], a0);
-            else
-              a1 = fma_t(win[i][(u + j) % PW], ref[i * PW + j], a1);
-          }
-        const T arg = a0 + a1;
-        const T k = Math<T>::exp_arg(arg);
-        f(q, k, arg, [&](int i, int j) -> T { return win[i][(u + j) % PW]; });
+  for (int c = 0; c < 2 * PW - 1; ++c) {
+    T x[PH];
+#pragma unroll
+    for (int i = 0; i < PH; ++i) x[i] = col0[i * Wd + c];
+#pragma unroll
+    for (int u = 0; u < PW; ++u) {
+      const int j = c - u;
+      if (j >= 0 && j < PW) {
+#pragma unroll
+        for (int i = 0; i < PH; ++i) acc[i * PW + j] = fma_t(coef[u], x[i], acc[i * PW + j]);
       }
     }
   }
@@ -248,24 +274,32 @@ __global__ void __launch_bounds__(kMaxTPB) kuf_fast_kernel(const FastParams<T> p
     const T* erow = e + c * p.Pc + r * p.Wout;
     const int woff = (p.w_per_plane ? c * p.Pc : 0) + r * p.Wout;
     const T* wrow = w + woff;
-    if (!BWD) {
+    const T* row0 = plane + r * p.Wd;
+    if constexpr (!BWD) {
       T rowacc = T(0);
-      sweep_row<T, PH, PW>(plane, p.Wd, r, p.Wout, ref, e_ref, erow,
-                           [&](int q, T k, T, auto) { rowacc = fma_t(wrow[q], k, rowacc); });
+      for (int q0 = 0; q0 < p.Wout; q0 += PW) {
+        T arg[PW], k[PW];
+        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, arg, k);
+#pragma unroll
+        for (int u = 0; u < PW; ++u) rowacc += (q0 + u < p.Wout) ? wrow[q0 + u] * k[u] : T(0);
+      }
       acc = fma_t(rowacc, sig2, acc);
     } else {
       T* sw = scratch + (warp * 32 + lane) * WP;
-      sweep_row<T, PH, PW>(plane, p.Wd, r, p.Wout, ref, e_ref, erow, [&](int q, T k, T arg, auto xget) {
-        const T v = Gm * k;
-        if (do_dw) sw[q] = v;
-        const T coef = v * wrow[q];
-        s0 += coef;
-        s2 = fma_t(coef, arg, s2);
+      for (int q0 = 0; q0 < p.Wout; q0 += PW) {
+        T arg[PW], k[PW], coef[PW];
+        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, arg, k);
 #pragma unroll
-        for (int i = 0; i < PH; ++i)
-#pragma unroll
-          for (int j = 0; j < PW; ++j) dz[i * PW + j] = fma_t(coef, xget(i, j), dz[i * PW + j]);
-      });
+        for (int u = 0; u < PW; ++u) {
+          const bool valid = q0 + u < p.Wout;
+          const T v = valid ? Gm * k[u] : T(0);
+          if (do_dw && valid) sw[q0 + u] = v;
+          coef[u] = valid ? v * wrow[q0 + u] : T(0);
+          s0 += coef[u];
+          s2 = fma_t(coef[u], valid ? arg[u] : T(0), s2);
+        }
+        group_accum<T, PH, PW>(row0 + q0, p.Wd, coef, dz);
+      }
       if (do_dw) {
         __syncwarp();
         const T* sc = scratch + warp * 32 * WP;
@@ -427,21 +461,32 @@ __global__ void __launch_bounds__(kMaxTPB) kdiag_fast_kernel(const FastParams<T>
     const T* erow = e + cs * p.Pc + rs * p.Wout;
     const int woff = (p.w_per_plane ? cs * p.Pc : 0) + rs * p.Wout;
     const T* wrow = w + woff;
-    if (!BWD) {
+    const T* row0 = plane + rs * p.Wd;
+    if constexpr (!BWD) {
       T rowacc = T(0);
-      sweep_row<T, PH, PW>(plane, p.Wd, rs, p.Wout, ref, e_ref, erow,
-                           [&](int q, T k, T, auto) { rowacc = fma_t(wrow[q], k, rowacc); });
+      for (int q0 = 0; q0 < p.Wout; q0 += PW) {
+        T arg[PW], k[PW];
+        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, arg, k);
+#pragma unroll
+        for (int u = 0; u < PW; ++u) rowacc += (q0 + u < p.Wout) ? wrow[q0 + u] * k[u] : T(0);
+      }
       acc = fma_t((T)wt, rowacc, acc);
     } else {
       T* sw = scratch + (warp * 32 + lane) * WP;
       const T wsc = (wt == 2) ? wp : T(0);
       T rowacc = T(0), rowacc2 = T(0);
-      sweep_row<T, PH, PW>(plane, p.Wd, rs, p.Wout, ref, e_ref, erow, [&](int q, T k, T arg, auto) {
-        const T wk = wrow[q] * k;
-        rowacc += wk;
-        rowacc2 = fma_t(wk, arg, rowacc2);
-        if (do_dw) sw[q] = wsc * k;
-      });
+      for (int q0 = 0; q0 < p.Wout; q0 += PW) {
+        T arg[PW], k[PW];
+        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, arg, k);
+#pragma unroll
+        for (int u = 0; u < PW; ++u) {
+          const bool valid = q0 + u < p.Wout;
+          const T wk = valid ? wrow[q0 + u] * k[u] : T(0);
+          rowacc += wk;
+          rowacc2 = fma_t(wk, valid ? arg[u] : T(0), rowacc2);
+          if (do_dw && valid) sw[q0 + u] = wsc * k[u];
+        }
+      }
       acc = fma_t((T)wt, rowacc, acc);
       acc2 = fma_t((T)wt, rowacc2, acc2);
       if (wt > 0) dwown += rowacc;

@@ -1,0 +1,79 @@
+"""The hot path as one unit of work: Kuf + Kdiag + Kuu forward and their backward for one
+minibatch, driven straight through the C ABI with pre-allocated buffers (no autograd tape).
+
+This is what a data-parallel rank runs per step: its shard of the minibatch rows, replicated
+parameters, and ONE packed gradient buffer [dZ | dW | dvariance | dlengthscales] that the NCCL
+all-reduce sums across ranks.  ``step()`` is stream-ordered and allocation-free, so
+it can be captured in a CUDA graph (``capture()``)."""
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+class HotPath:
+    def __init__(self, spec, X, Z, W, variance, lengthscales, G, gd, Gu, diag_add=0.0):
+        self.spec = spec
+        self.X, self.Z, self.W = X.contiguous(), Z.contiguous(), None if W is None else W.contiguous()
+        self.variance, self.lengthscales = variance.contiguous(), lengthscales.contiguous()
+        self.G, self.gd, self.Gu = G.contiguous(), gd.contiguous(), Gu.contiguous()
+        self.diag_add = float(diag_add)
+        dev, dt = X.device, X.dtype
+        N, M = X.shape[0], Z.shape[0]
+        self.N, self.M = N, M
+        C = spec.C
+        self.Kuf = torch.empty((M, N, C) if spec.per_channel else (M, N), dtype=dt, device=dev)
+        self.Kdiag = torch.empty((N, C) if spec.per_channel else (N,), dtype=dt, device=dev)
+        self.Kuu = torch.empty((M, M), dtype=dt, device=dev)
+        sizes = [Z.numel(), 0 if W is None else W.numel(), variance.numel(), lengthscales.numel()]
+        self.grads = torch.zeros(sum(sizes), dtype=dt, device=dev)
+        o = 0
+        views = []
+        for s in sizes:
+            views.append(self.grads[o:o + s] if s else None)
+            o += s
+        self.dZ, self.dW, self.dvar, self.dls = views
+        self.ws, self.ws_bytes = spec.workspace(N, M, dev)
+        self.graph = None
+        self.kernels_per_step = 6
+
+    def forward(self):
+        L, s, st = _lib.lib(), self.spec, stream_ptr()
+        check(L.cgp_kuf_fwd(s.ref(), self.N, self.M, ptr(self.X), ptr(self.Z), ptr(self.W), ptr(self.variance),
+                            ptr(self.lengthscales), ptr(self.Kuf), ptr(self.ws), self.ws_bytes, st))
+        check(L.cgp_kdiag_fwd(s.ref(), self.N, ptr(self.X), ptr(self.W), ptr(self.variance), ptr(self.lengthscales),
+                              ptr(self.Kdiag), ptr(self.ws), self.ws_bytes, st))
+        check(L.cgp_kuu_fwd(s.ref(), self.M, ptr(self.Z), ptr(self.variance), ptr(self.lengthscales), self.diag_add,
+                            ptr(self.Kuu), st))
+
+    def backward(self):
+        L, s, st = _lib.lib(), self.spec, stream_ptr()
+        self.grads.zero_()
+        check(L.cgp_kuf_bwd(s.ref(), self.N, self.M, ptr(self.X), ptr(self.Z), ptr(self.W), ptr(self.variance),
+                            ptr(self.lengthscales), ptr(self.G), ptr(self.dZ), ptr(self.dW), ptr(self.dvar),
+                            ptr(self.dls), ptr(self.ws), self.ws_bytes, st))
+        check(L.cgp_kdiag_bwd(s.ref(), self.N, ptr(self.X), ptr(self.W), ptr(self.variance), ptr(self.lengthscales),
+                              ptr(self.gd), ptr(self.dW), ptr(self.dvar), ptr(self.dls), ptr(self.ws),
+                              self.ws_bytes, st))
+        check(L.cgp_kuu_bwd(s.ref(), self.M, ptr(self.Z), ptr(self.variance), ptr(self.lengthscales), ptr(self.Gu),
+                            ptr(self.dZ), ptr(self.dvar), ptr(self.dls), st))
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.forward()
+            self.backward()
+
+    def capture(self):
+        """Capture forward+backward into a CUDA graph (launch-latency matters: the whole step is
+        ~1 ms of GPU time at the MNIST shape)."""
+        self.forward()
+        self.backward()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward()
+            self.backward()
+        self.graph = g
+        return g
