@@ -151,6 +151,7 @@ static size_t fast_smem(const FastParams<T>& p, int tpb, bool bwd) {
   size_t n = (size_t)p.C * p.H * p.Wd + (size_t)p.C * p.Pc + nW;
   if (bwd) n += nW + (size_t)(tpb / 32) * 32 * (p.Wout | 1);
   n += 32;  // block_sum scratch
+  n += Math<T>::kTableDoubles;  // exp table
   return n * sizeof(T);
 }
 
@@ -300,7 +301,7 @@ static int run_kuu_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int M,
   p.JT = JT;
   const int njc = (M + JT - 1) / JT;
   const int Dp = d->ph * d->pw;
-  const size_t smem = sizeof(T) * ((size_t)JT * Dp + JT);
+  const size_t smem = sizeof(T) * ((size_t)JT * Dp + JT + Math<T>::kTableDoubles);
   dim3 grid(nic, njc);
 #define CALL(PH_, PW_) kuu_fast_kernel<T, PH_ * PW_, BWD><<<grid, kKuuTPB, smem, st>>>(p)
   CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)

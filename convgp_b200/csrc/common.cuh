@@ -20,50 +20,58 @@ int num_sms();
   } while (0)
 
 // ---------------------------------------------------------------- math traits
-// exp() of a non-positive-ish argument.  double: Cody-Waite reduction + degree-11 polynomial
-// on the FP64 pipe (no branches, flushes below 2^-1022 to ~1e-308 which is zero at the 1e-10
-// parity tolerance).  float: arguments are carried in log2 units so the evaluation is one MUFU.
+// exp() of a non-positive-ish argument.  double: table-driven (128-entry 2^(j/128) in shared
+// memory) + degree-4 polynomial, 8 FP64-pipe instructions, branch-free.  float: arguments are
+// carried in log2 units so the evaluation is one MUFU ex2.
 template <typename T>
 struct Math;
+
+constexpr int kExpTableBits = 7;
+constexpr int kExpTable = 1 << kExpTableBits;  // entries of 2^(j/128)
 
 template <>
 struct Math<double> {
   // Arguments of exp are carried in natural units.
   static constexpr double kArgScale = 1.0;
-  static __device__ __forceinline__ double exp_arg(double x) {
-    const double kLog2e = 1.4426950408889634074;
-    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
-    const double kLn2Hi = 6.93147180369123816490e-01;
-    const double kLn2Lo = 1.90821492927058770002e-10;
-    double t = fma(x, kLog2e, kMagic);
-    int ki = __double2loint(t);
-    double kf = t - kMagic;
-    double r = fma(kf, -kLn2Hi, x);
-    r = fma(kf, -kLn2Lo, r);
-    // exp(r), |r| <= ln2/2: Taylor to degree 11 (truncation < 7e-15 relative)
-    double p = 2.50521083854417187751e-08;        // 1/11!
-    p = fma(p, r, 2.75573192239858906526e-07);    // 1/10!
-    p = fma(p, r, 2.75573192239858906526e-06);    // 1/9!
-    p = fma(p, r, 2.48015873015873015873e-05);    // 1/8!
-    p = fma(p, r, 1.98412698412698412698e-04);    // 1/7!
-    p = fma(p, r, 1.38888888888888888889e-03);    // 1/6!
-    p = fma(p, r, 8.33333333333333333333e-03);    // 1/5!
-    p = fma(p, r, 4.16666666666666666667e-02);    // 1/4!
-    p = fma(p, r, 1.66666666666666666667e-01);    // 1/3!
+  static constexpr int kTableDoubles = kExpTable;
+
+  // tbl[j] = 2^(j/128), j < 128, correctly rounded (filled once per CTA by init_table).
+  static __device__ __forceinline__ void init_table(double* tbl) {
+    for (int j = threadIdx.x; j < kExpTable; j += blockDim.x) tbl[j] = exp2((double)j / kExpTable);
+  }
+
+  // exp(x) = 2^k * 2^(j/128) * exp(r),  n = rint(x * 128/ln2) = 128 k + j,  r = x - n ln2/128,
+  // |r| <= ln2/256 so a degree-4 Taylor polynomial truncates below 1.3e-15 relative.  8 FP64-pipe
+  // instructions; the table lookup (shared memory) and the exponent patch run on other pipes.
+  // One-step reduction with the full-precision constant: the error n * ulp(ln2/128) stays below
+  // 3e-15 for every argument whose exp is above 1e-10 of the largest term (the parity scale).
+  // Results below 2^-1021 are flushed to ~1e-308; no branches.
+  static __device__ __forceinline__ double exp_arg(double x, const double* __restrict__ tbl) {
+    const double kInvC = 184.6649652337873;        // 128 / ln 2
+    const double kC = 5.4152123481245727e-03;      // ln 2 / 128
+    const double kMagic = 6755399441055744.0;      // 1.5 * 2^52
+    const double t = fma(x, kInvC, kMagic);
+    const int n = __double2loint(t);
+    const double nf = t - kMagic;
+    const double r = fma(nf, -kC, x);
+    double p = 4.16666666666666666667e-02;         // 1/4!
+    p = fma(p, r, 1.66666666666666666667e-01);     // 1/3!
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    ki = max(ki, -1021);  // integer pipe; keeps the exponent patch below in the normal range
-    int hi = __double2hiint(p) + (ki << 20);
-    return __hiloint2double(hi, __double2loint(p));
+    p *= tbl[n & (kExpTable - 1)];
+    const int k = max(n >> kExpTableBits, -1021);  // integer pipe; keeps the patched exponent normal
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
   }
 };
 
 template <>
 struct Math<float> {
-  // Arguments of exp are carried pre-multiplied by log2(e): exp(x) == ex2(x * log2e).
+  // Arguments of exp are carried pre-multiplied by log2(e): exp(x) == ex2(x * log2e), one MUFU.
   static constexpr float kArgScale = 1.4426950408889634074f;
-  static __device__ __forceinline__ float exp_arg(float x) {
+  static constexpr int kTableDoubles = 0;
+  static __device__ __forceinline__ void init_table(float*) {}
+  static __device__ __forceinline__ float exp_arg(float x, const float* __restrict__) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;

@@ -89,7 +89,8 @@ __device__ __forceinline__ void stage_image(const FastParams<T>& p, int n, T* im
 // arg[u] = e_ref + erow[q0 + u] + dot(ref, patch(q0 + u)),  k[u] = exp(arg[u])
 template <typename T, int PH, int PW>
 __device__ __forceinline__ void group_eval(const T* __restrict__ col0, int Wd, const T (&ref)[PH * PW], T e_ref,
-                                           const T* __restrict__ erow_q0, T (&arg)[PW], T (&k)[PW]) {
+                                           const T* __restrict__ erow_q0, const T* __restrict__ tbl, int nvalid,
+                                           T (&arg)[PW], T (&k)[PW]) {
   T a1[PW];
 #pragma unroll
   for (int u = 0; u < PW; ++u) {
@@ -115,8 +116,8 @@ __device__ __forceinline__ void group_eval(const T* __restrict__ col0, int Wd, c
   }
 #pragma unroll
   for (int u = 0; u < PW; ++u) {
-    arg[u] += a1[u];
-    k[u] = Math<T>::exp_arg(arg[u]);
+    arg[u] = (u < nvalid) ? arg[u] + a1[u] : T(0);  // masked patches evaluate exp(0): finite, weight 0
+    k[u] = Math<T>::exp_arg(arg[u], tbl);
   }
 }
 
@@ -145,10 +146,11 @@ __device__ __forceinline__ void group_accum(const T* __restrict__ col0, int Wd, 
 // contiguous range of (chunk, image, plane, patch-row) items.
 // =====================================================================================
 template <typename T, int PH, int PW, bool BWD>
-__global__ void __launch_bounds__(kMaxTPB) kuf_fast_kernel(const FastParams<T> p) {
+__global__ void __launch_bounds__(128, BWD ? (sizeof(T) == 8 ? 2 : 3) : 4) kuf_fast_kernel(const FastParams<T> p) {
   constexpr int D = PH * PW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* img = reinterpret_cast<T*>(smem_raw);
+  T* tbl = reinterpret_cast<T*>(smem_raw);  // exp table (double only)
+  T* img = tbl + Math<T>::kTableDoubles;
   T* e = img + p.C * p.H * p.Wd;
   const int nW = p.w_per_plane ? p.C * p.Pc : p.Pc;
   T* w = e + p.C * p.Pc;
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(kMaxTPB) kuf_fast_kernel(const FastParams<T> p
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool do_dw = BWD && p.dW != nullptr;
+  Math<T>::init_table(tbl);
   for (int i = tid; i < nW; i += blockDim.x) {
     w[i] = p.Wt ? p.Wt[i] : T(1);
     if (BWD) dWacc[i] = T(0);
@@ -279,24 +282,24 @@ __global__ void __launch_bounds__(kMaxTPB) kuf_fast_kernel(const FastParams<T> p
       T rowacc = T(0);
       for (int q0 = 0; q0 < p.Wout; q0 += PW) {
         T arg[PW], k[PW];
-        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, arg, k);
+        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, tbl, p.Wout - q0, arg, k);
 #pragma unroll
-        for (int u = 0; u < PW; ++u) rowacc += (q0 + u < p.Wout) ? wrow[q0 + u] * k[u] : T(0);
+        for (int u = 0; u < PW; ++u) rowacc = fma_t((q0 + u < p.Wout) ? wrow[q0 + u] : T(0), k[u], rowacc);
       }
       acc = fma_t(rowacc, sig2, acc);
     } else {
       T* sw = scratch + (warp * 32 + lane) * WP;
       for (int q0 = 0; q0 < p.Wout; q0 += PW) {
         T arg[PW], k[PW], coef[PW];
-        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, arg, k);
+        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, tbl, p.Wout - q0, arg, k);
 #pragma unroll
         for (int u = 0; u < PW; ++u) {
           const bool valid = q0 + u < p.Wout;
-          const T v = valid ? Gm * k[u] : T(0);
+          const T v = Gm * k[u];
           if (do_dw && valid) sw[q0 + u] = v;
-          coef[u] = valid ? v * wrow[q0 + u] : T(0);
+          coef[u] = v * (valid ? wrow[q0 + u] : T(0));
           s0 += coef[u];
-          s2 = fma_t(coef[u], valid ? arg[u] : T(0), s2);
+          s2 = fma_t(coef[u], arg[u], s2);
         }
         group_accum<T, PH, PW>(row0 + q0, p.Wd, coef, dz);
       }
@@ -337,7 +340,8 @@ template <typename T, int PH, int PW, bool BWD>
 __global__ void __launch_bounds__(kMaxTPB) kdiag_fast_kernel(const FastParams<T> p) {
   constexpr int D = PH * PW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* img = reinterpret_cast<T*>(smem_raw);
+  T* tbl = reinterpret_cast<T*>(smem_raw);  // exp table (double only)
+  T* img = tbl + Math<T>::kTableDoubles;
   T* e = img + p.C * p.H * p.Wd;
   const int nW = p.w_per_plane ? p.C * p.Pc : p.Pc;
   T* w = e + p.C * p.Pc;
@@ -348,6 +352,7 @@ __global__ void __launch_bounds__(kMaxTPB) kdiag_fast_kernel(const FastParams<T>
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool do_dw = BWD && p.dW != nullptr;
+  Math<T>::init_table(tbl);
   for (int i = tid; i < nW; i += blockDim.x) {
     w[i] = p.Wt ? p.Wt[i] : T(1);
     if (BWD) dWacc[i] = T(0);
@@ -466,9 +471,9 @@ __global__ void __launch_bounds__(kMaxTPB) kdiag_fast_kernel(const FastParams<T>
       T rowacc = T(0);
       for (int q0 = 0; q0 < p.Wout; q0 += PW) {
         T arg[PW], k[PW];
-        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, arg, k);
+        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, tbl, p.Wout - q0, arg, k);
 #pragma unroll
-        for (int u = 0; u < PW; ++u) rowacc += (q0 + u < p.Wout) ? wrow[q0 + u] * k[u] : T(0);
+        for (int u = 0; u < PW; ++u) rowacc = fma_t((q0 + u < p.Wout) ? wrow[q0 + u] : T(0), k[u], rowacc);
       }
       acc = fma_t((T)wt, rowacc, acc);
     } else {
@@ -477,13 +482,13 @@ __global__ void __launch_bounds__(kMaxTPB) kdiag_fast_kernel(const FastParams<T>
       T rowacc = T(0), rowacc2 = T(0);
       for (int q0 = 0; q0 < p.Wout; q0 += PW) {
         T arg[PW], k[PW];
-        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, arg, k);
+        group_eval<T, PH, PW>(row0 + q0, p.Wd, ref, e_ref, erow + q0, tbl, p.Wout - q0, arg, k);
 #pragma unroll
         for (int u = 0; u < PW; ++u) {
           const bool valid = q0 + u < p.Wout;
-          const T wk = valid ? wrow[q0 + u] * k[u] : T(0);
+          const T wk = (valid ? wrow[q0 + u] : T(0)) * k[u];
           rowacc += wk;
-          rowacc2 = fma_t(wk, valid ? arg[u] : T(0), rowacc2);
+          rowacc2 = fma_t(wk, arg[u], rowacc2);
           if (do_dw && valid) sw[q0 + u] = wsc * k[u];
         }
       }

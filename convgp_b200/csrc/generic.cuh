@@ -47,9 +47,14 @@ __device__ __forceinline__ void stage_scales(const GenParams<T>& p, T* a) {
 }
 
 template <typename T>
-__device__ __forceinline__ T exp_neg_half(T r2) {
-  return Math<T>::exp_arg(T(-0.5) * Math<T>::kArgScale * r2);
+__device__ __forceinline__ T exp_neg_half(T r2, const T* tbl) {
+  return Math<T>::exp_arg(T(-0.5) * Math<T>::kArgScale * r2, tbl);
 }
+
+// exp table in static shared memory (double only); callers __syncthreads() before first use
+#define CGP_GENERIC_EXP_TABLE()                                                         \
+  __shared__ T tbl[Math<T>::kTableDoubles > 0 ? Math<T>::kTableDoubles : 1];            \
+  Math<T>::init_table(tbl)
 
 // --------------------------------------------------------------------------- patches
 template <typename T>
@@ -108,6 +113,7 @@ __global__ void __launch_bounds__(kGenTPB) generic_kuf_kernel(const GenParams<T>
   T* dAt = At + D * kGenTPB;                  // BWD: [D][TPB]
   T* dL = dAt + (BWD ? D * kGenTPB : 0);      // BWD && ard: [G*D][TPB]
   __shared__ T red[kGenTPB / 32];
+  CGP_GENERIC_EXP_TABLE();
 
   const int m = blockIdx.x * kGenTPB + tid, n = blockIdx.y;
   const bool active = m < p.M;
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(kGenTPB) generic_kuf_kernel(const GenParams<T>
       T ks = T(0);
 #pragma unroll
       for (int g = 0; g < kMaxGroups; ++g)
-        if (g < G) ks = fma_t(var[g], exp_neg_half(r2[g]), ks);
+        if (g < G) ks = fma_t(var[g], exp_neg_half(r2[g], tbl), ks);
       acc = fma_t(wv, ks, acc);
     } else {
       const size_t o = p.per_channel ? ((size_t)m * p.N + n) * p.C + c : (size_t)m * p.N + n;
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(kGenTPB) generic_kuf_kernel(const GenParams<T>
       for (int g = 0; g < kMaxGroups; ++g) {
         cg[g] = T(0);
         if (g < G) {
-          const T kt = exp_neg_half(r2[g]);
+          const T kt = exp_neg_half(r2[g], tbl);
           ks = fma_t(var[g], kt, ks);
           dv[g] = fma_t(gm * wv, kt, dv[g]);
           cg[g] = gm * wv * kt * var[g];
@@ -227,6 +233,7 @@ __global__ void __launch_bounds__(kGenTPB) generic_kxx_kernel(const GenParams<T>
   T* At = a + G * D;
   T* dL = At + D * kGenTPB;  // BWD && ard
   __shared__ T red[kGenTPB / 32];
+  CGP_GENERIC_EXP_TABLE();
 
   const int pp = blockIdx.x * kGenTPB + tid;
   const int n = p.diag_only ? blockIdx.y : blockIdx.y / p.N2;
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(kGenTPB) generic_kxx_kernel(const GenParams<T>
     for (int g = 0; g < kMaxGroups; ++g) {
       cg[g] = T(0);
       if (g < G) {
-        const T kt = exp_neg_half(r2[g]);
+        const T kt = exp_neg_half(r2[g], tbl);
         ks = fma_t(var[g], kt, ks);
         if (BWD) {
           dv[g] = fma_t(gn * wp * wq, kt, dv[g]);
@@ -328,6 +335,7 @@ __global__ void generic_kuu_fwd_kernel(const GenParams<T> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int G = p.gs.G, D = p.gs.D;
   T* a = reinterpret_cast<T*>(smem_raw);
+  CGP_GENERIC_EXP_TABLE();
   stage_scales(p, a);
   __syncthreads();
   const size_t total = (size_t)p.M * p.M;
@@ -343,7 +351,7 @@ __global__ void generic_kuu_fwd_kernel(const GenParams<T> p) {
         const T diff = zi[d] - zj[d];
         r2 = fma_t(a[g * D + d], diff * diff, r2);
       }
-      ks = fma_t(p.var[g], exp_neg_half(r2), ks);
+      ks = fma_t(p.var[g], exp_neg_half(r2, tbl), ks);
     }
     if (i == j) ks += (T)p.diag_add;
     p.out[idx] = ks;
@@ -356,6 +364,7 @@ __global__ void generic_kuu_bwd_kernel(const GenParams<T> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int G = p.gs.G, D = p.gs.D;
   T* a = reinterpret_cast<T*>(smem_raw);
+  CGP_GENERIC_EXP_TABLE();
   stage_scales(p, a);
   __syncthreads();
   const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -379,7 +388,7 @@ __global__ void generic_kuu_bwd_kernel(const GenParams<T> p) {
           const T diff = zi[k] - zj[k];
           r2 = fma_t(a[g * D + k], diff * diff, r2);
         }
-        const T kt = exp_neg_half(r2);
+        const T kt = exp_neg_half(r2, tbl);
         const T kv = p.var[g] * kt;
         dz = fma_t(gsym * kv * a[g * D + d], dd, dz);
         if (p.gs.ard) {

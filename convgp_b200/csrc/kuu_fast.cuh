@@ -27,7 +27,8 @@ struct KuuParams {
 template <typename T, int D, bool BWD>
 __global__ void __launch_bounds__(kKuuTPB) kuu_fast_kernel(const KuuParams<T> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* zj = reinterpret_cast<T*>(smem_raw);  // [JT][D]
+  T* tbl = reinterpret_cast<T*>(smem_raw);  // exp table (double only)
+  T* zj = tbl + Math<T>::kTableDoubles;    // [JT][D]
   T* ej = zj + p.JT * D;                   // [JT]
   __shared__ T red[kKuuTPB / 32];
   const int tid = threadIdx.x;
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(kKuuTPB) kuu_fast_kernel(const KuuParams<T> p)
   const bool active = i < p.M;
   const int j0 = blockIdx.y * p.JT;
   const int jn = min(p.JT, p.M - j0);
+  Math<T>::init_table(tbl);
 
   for (int c = 0; c < p.nplanes; ++c) {
     const int g = p.grp_per_plane ? c : 0;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(kKuuTPB) kuu_fast_kernel(const KuuParams<T> p)
 #pragma unroll
       for (int u = 0; u < kKuuJG; ++u) {
         arg[u] += a1[u];
-        k[u] = Math<T>::exp_arg(arg[u]);
+        k[u] = Math<T>::exp_arg(arg[u], tbl);
       }
       if constexpr (!BWD) {
 #pragma unroll

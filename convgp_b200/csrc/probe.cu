@@ -10,6 +10,11 @@ constexpr int kChains = 8;
 template <int KIND>
 __global__ void __launch_bounds__(256) probe_kernel(int iters, double* sink, double seed) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double tbl[kExpTable];
+  if (KIND == 3) {
+    Math<double>::init_table(tbl);
+    __syncthreads();
+  }
   if (KIND == 0) {  // FP64 FMA
     double a[kChains], b = 1.0 + seed * 1e-9, c = seed * 1e-12;
 #pragma unroll
@@ -38,7 +43,7 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, double* sink, dou
     for (int i = 0; i < kChains; ++i) a[i] = -(float)seed - i * 0.1f - tid * 1e-6f;
     for (int it = 0; it < iters; ++it)
 #pragma unroll
-      for (int i = 0; i < kChains; ++i) a[i] = -Math<float>::exp_arg(a[i]);
+      for (int i = 0; i < kChains; ++i) a[i] = -Math<float>::exp_arg(a[i], nullptr);
     float s = 0;
 #pragma unroll
     for (int i = 0; i < kChains; ++i) s += a[i];
@@ -49,7 +54,7 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, double* sink, dou
     for (int i = 0; i < kChains; ++i) a[i] = -seed - i * 0.1 - tid * 1e-6;
     for (int it = 0; it < iters; ++it)
 #pragma unroll
-      for (int i = 0; i < kChains; ++i) a[i] = -Math<double>::exp_arg(a[i]);
+      for (int i = 0; i < kChains; ++i) a[i] = -Math<double>::exp_arg(a[i], tbl);
     double s = 0;
 #pragma unroll
     for (int i = 0; i < kChains; ++i) s += a[i];
