@@ -85,6 +85,16 @@ __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { 
 template <>
 __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 
+// acc = a * b + acc with the instruction ORDER pinned (volatile).  The FP64 pipe only reaches its
+// rate (one warp FMA / ~2.3 cycles per sub-partition, probed) when an FMA brings at most two new
+// 64-bit register operands; with three it drops to ~3.3 cycles (register-file read bandwidth,
+// probe kinds 9/10).  The hot loops therefore issue runs of FMAs that share the `a` operand so it
+// is served by the operand-reuse cache; pinning the order keeps ptxas from interleaving the runs.
+__device__ __forceinline__ void fma_pinned(double a, double b, double& acc) {
+  asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void fma_pinned(float a, float b, float& acc) { acc = fmaf(a, b, acc); }
+
 // ---------------------------------------------------------------- reductions
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

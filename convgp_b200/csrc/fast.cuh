@@ -87,57 +87,47 @@ __device__ __forceinline__ void stage_image(const FastParams<T>& p, int n, T* im
 // (initialised) shared memory just past the row and are masked with selects, never multiplied.
 
 // arg[u] = e_ref + erow[q0 + u] + dot(ref, patch(q0 + u)),  k[u] = exp(arg[u])
+// Row-streaming: for each patch row i the 2*PW-1 pixels the group touches are loaded once, then
+// for every reference element ref[i][j] a run of PW FMAs (one per patch) shares it as operand --
+// 80% of the FMAs bring only two new register operands (see fma_pinned) and the PW accumulators
+// are PW independent chains.
 template <typename T, int PH, int PW>
 __device__ __forceinline__ void group_eval(const T* __restrict__ col0, int Wd, const T (&ref)[PH * PW], T e_ref,
                                            const T* __restrict__ erow_q0, const T* __restrict__ tbl, int nvalid,
                                            T (&arg)[PW], T (&k)[PW]) {
-  T a1[PW];
 #pragma unroll
-  for (int u = 0; u < PW; ++u) {
-    arg[u] = e_ref + erow_q0[u];
-    a1[u] = T(0);
-  }
+  for (int u = 0; u < PW; ++u) arg[u] = e_ref + erow_q0[u];
 #pragma unroll
-  for (int c = 0; c < 2 * PW - 1; ++c) {
-    T x[PH];
+  for (int i = 0; i < PH; ++i) {
+    T x[2 * PW - 1];
 #pragma unroll
-    for (int i = 0; i < PH; ++i) x[i] = col0[i * Wd + c];
+    for (int c = 0; c < 2 * PW - 1; ++c) x[c] = col0[i * Wd + c];
 #pragma unroll
-    for (int u = 0; u < PW; ++u) {
-      const int j = c - u;
-      if (j >= 0 && j < PW) {
+    for (int j = 0; j < PW; ++j)
 #pragma unroll
-        for (int i = 0; i < PH; ++i) {
-          if ((i & 1) == 0) arg[u] = fma_t(x[i], ref[i * PW + j], arg[u]);
-          else a1[u] = fma_t(x[i], ref[i * PW + j], a1[u]);
-        }
-      }
-    }
+      for (int u = 0; u < PW; ++u) fma_pinned(ref[i * PW + j], x[u + j], arg[u]);
   }
 #pragma unroll
   for (int u = 0; u < PW; ++u) {
-    arg[u] = (u < nvalid) ? arg[u] + a1[u] : T(0);  // masked patches evaluate exp(0): finite, weight 0
+    arg[u] = (u < nvalid) ? arg[u] : T(0);  // masked patches evaluate exp(0): finite, weight 0
     k[u] = Math<T>::exp_arg(arg[u], tbl);
   }
 }
 
-// acc[i*PW + j] += sum_u coef[u] * patch(q0 + u)[i][j]   (second pass over the same columns)
+// acc[i*PW + j] += sum_u coef[u] * patch(q0 + u)[i][j]   (second pass over the same pixels; runs of
+// PW FMAs share coef[u])
 template <typename T, int PH, int PW>
 __device__ __forceinline__ void group_accum(const T* __restrict__ col0, int Wd, const T (&coef)[PW],
                                             T (&acc)[PH * PW]) {
 #pragma unroll
-  for (int c = 0; c < 2 * PW - 1; ++c) {
-    T x[PH];
+  for (int i = 0; i < PH; ++i) {
+    T x[2 * PW - 1];
 #pragma unroll
-    for (int i = 0; i < PH; ++i) x[i] = col0[i * Wd + c];
+    for (int c = 0; c < 2 * PW - 1; ++c) x[c] = col0[i * Wd + c];
 #pragma unroll
-    for (int u = 0; u < PW; ++u) {
-      const int j = c - u;
-      if (j >= 0 && j < PW) {
+    for (int u = 0; u < PW; ++u)
 #pragma unroll
-        for (int i = 0; i < PH; ++i) acc[i * PW + j] = fma_t(coef[u], x[i], acc[i * PW + j]);
-      }
-    }
+      for (int j = 0; j < PW; ++j) fma_pinned(coef[u], x[u + j], acc[i * PW + j]);
   }
 }
 

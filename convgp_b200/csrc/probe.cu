@@ -15,7 +15,57 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, double* sink, dou
     Math<double>::init_table(tbl);
     __syncthreads();
   }
-  if (KIND == 0) {  // FP64 FMA
+  if (KIND == 9 || KIND == 10) {  // FP64 FMA with three distinct register operands (9) / one shared multiplier (10)
+    double a[kChains], b[kChains], c[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+      a[i] = seed + i + tid * 1e-6;
+      b[i] = 1.0 + (seed + i) * 1e-9 + tid * 1e-12;
+      c[i] = (seed + i) * 1e-12 + tid * 1e-15;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < kChains; ++i) {
+        if (KIND == 9) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[i]) : "d"(b[i]), "d"(c[i]));
+        else asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[i]) : "d"(b[0]), "d"(c[i]));
+      }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i] + b[i] + c[i];
+    if (s == 12345.678) sink[0] = s;
+  } else if (KIND == 7 || KIND == 8) {  // FP64 FMA chains + as many independent integer (7) / shared-load (8) instructions
+    __shared__ double sm[256];
+    sm[threadIdx.x] = seed + threadIdx.x;
+    __syncthreads();
+    double a[kChains], b = 1.0 + seed * 1e-9, c = seed * 1e-12;
+    unsigned x[kChains];
+    double ld = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+      a[i] = seed + i + tid * 1e-6;
+      x[i] = tid * 7 + i;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < kChains; ++i) {
+        a[i] = fma(a[i], b, c);
+        if (KIND == 7) x[i] = x[i] * 1664525u + 1013904223u;
+        else ld += sm[(x[i] + it) & 255];
+      }
+    }
+    double s = ld;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i] + (double)x[i];
+    if (s == 12345.678) sink[0] = s;
+  } else if (KIND == 6) {  // FP64 FMA dependent-issue latency: ONE chain per thread, one warp per SM sub-partition
+    double a = seed + tid * 1e-6, b = 1.0 + seed * 1e-9, c = seed * 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a = fma(a, b, c);
+    }
+    if (a == 12345.678) sink[0] = a;
+  } else if (KIND == 0) {  // FP64 FMA
     double a[kChains], b = 1.0 + seed * 1e-9, c = seed * 1e-12;
 #pragma unroll
     for (int i = 0; i < kChains; ++i) a[i] = seed + i + tid * 1e-6;
@@ -91,7 +141,7 @@ template <int KIND>
 static int run_probe(double ops_per_thread_iter, double* result) {
   double* sink = nullptr;
   CGP_CUDA_CHECK(cudaMalloc(&sink, sizeof(double)));
-  const int blocks = num_sms() * 8, threads = 256;
+  const int blocks = KIND == 6 ? num_sms() : num_sms() * 8, threads = KIND == 6 ? 128 : 256;
   const int iters = (KIND == 3) ? 512 : (KIND >= 4 ? 1024 : 4096);
   cudaEvent_t e0, e1;
   CGP_CUDA_CHECK(cudaEventCreate(&e0));
@@ -131,6 +181,14 @@ extern "C" int cgp_peak_probe(int32_t kind, double* ops_per_s) {
     // one m8n8k4 mma = 256 FMAs per warp = 8 per thread
     case 4: return run_probe<4>(kChains * 8.0, ops_per_s);
     case 5: return run_probe<5>(kChains * (8.0 + 4.0), ops_per_s);
+    // dependent chain, one warp per sub-partition: cycles per FMA = 128 * SMs * clock / result
+    case 6: return run_probe<6>(16.0, ops_per_s);
+    // FMAs per second while an equal number of integer (7) / LDS (8) instructions is co-issued
+    case 7: return run_probe<7>(kChains, ops_per_s);
+    case 8: return run_probe<8>(kChains, ops_per_s);
+    // register-file read bandwidth: three distinct 64-bit operands per FMA (9), one of them shared (10)
+    case 9: return run_probe<9>(kChains, ops_per_s);
+    case 10: return run_probe<10>(kChains, ops_per_s);
     default:
       set_error("unknown probe kind %d", kind);
       return CGP_ERR_BAD_DESC;

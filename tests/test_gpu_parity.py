@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import Case, rel_err
+from tests.util import Case, longdouble_kuf, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -49,8 +49,15 @@ def test_forward_and_backward_match_oracle(case, dtype):
     tol = TOL[dtype]
     ok = case.oracle_kernel()
     ref = case.twin_grads()
-    # the twin is itself checked against the NumPy oracle here (values)
-    assert rel_err(ref["kuf"], ok.Kzx(case.Z, case.X)) < 1e-12
+    # the twin is itself checked against the NumPy oracle here (values); on disagreement say which
+    # of the two CPU stacks drifted from an extended-precision evaluation of the same formula
+    okuf = ok.Kzx(case.Z, case.X)
+    if rel_err(ref["kuf"], okuf) >= 1e-12:
+        import torch as _t
+        ld = longdouble_kuf(case)
+        pytest.fail("CPU oracles disagree: twin-vs-numpy %.3g, numpy-vs-longdouble %.3g, twin-vs-longdouble %.3g "
+                    "(torch threads %d)" % (rel_err(ref["kuf"], okuf), rel_err(okuf, ld), rel_err(ref["kuf"], ld),
+                                            _t.get_num_threads()))
     assert rel_err(ref["kdiag"], ok.Kdiag(case.X)) < 1e-12
     got = case.package_grads(dtype)
     for key in ("kuf", "kdiag", "kuu", "dZ"):

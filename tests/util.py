@@ -14,6 +14,27 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / (denom if denom > 0 else 1.0))
 
 
+def longdouble_kuf(case):
+    """Kzx in extended precision with the direct (a-b)^2 distance: the arbiter when two float64 CPU
+    implementations disagree."""
+    ok = case.oracle_kernel()
+    g = case.geom
+    Xp = ok._get_patches(case.X).reshape(-1, g.D).astype(np.longdouble)
+    Z = case.Z.astype(np.longdouble)
+    tot = 0
+    for (v, l, ad, ard) in case.groups:
+        idx = np.arange(g.D) if ad is None else np.arange(g.D)[ad]
+        ls = np.asarray(l, dtype=np.longdouble)
+        d = (((Z[:, None, idx] - Xp[None, :, idx]) / ls) ** 2).sum(-1)
+        tot = tot + np.longdouble(v) * np.exp(-d / 2)
+    Wv = np.ones(case.wshape()) if case.Wv is None else case.Wv
+    M, N = case.M, case.N
+    if case.kind == "multi":
+        big = tot.reshape(M, N, case.C, g.Pc)
+        return (np.einsum('mncp,cp->mnc', big, Wv.astype(np.longdouble)) / g.P).astype(np.float64)
+    return ((tot.reshape(M, N, g.P) * Wv.astype(np.longdouble)).sum(2) / g.P).astype(np.float64)
+
+
 class Case:
     """One kernel configuration.  groups: list of (variance, lengthscales, active_dims|None, ARD)."""
 
