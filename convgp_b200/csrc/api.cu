@@ -1,14 +1,17 @@
 // C-ABI entry points of libconvgp_b200.so: validation, path selection, launch configuration.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 
 #include "fast.cuh"
 #include "kuu_fast.cuh"
+#include "mma64.cuh"
 #include "generic.cuh"
 
 namespace cgp {
@@ -155,6 +158,23 @@ static size_t fast_smem(const FastParams<T>& p, int tpb, bool bwd) {
   return n * sizeof(T);
 }
 
+// Tuning knobs (development only; read once): CGP_KUF_FWD / CGP_KUF_BWD / CGP_KDIAG_FWD / CGP_KDIAG_BWD
+// = "mma" | "fma" select the float64 kernel family, CGP_KDIAG_WARPS caps warps per CTA.
+static int env_choice(const char* name, int dflt) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  if (!strcmp(v, "mma")) return 1;
+  if (!strcmp(v, "fma")) return 0;
+  return atoi(v);
+}
+
+template <typename T>
+static size_t mma_smem(const FastParams<T>& p, bool bwd) {
+  size_t nW = p.w_per_plane ? (size_t)p.C * p.Pc : (size_t)p.Pc;
+  size_t n = (size_t)p.C * p.H * p.Wd + (size_t)p.C * p.Pc + nW + (bwd ? nW : 0) + 32 + Math<T>::kTableDoubles;
+  return n * sizeof(T);
+}
+
 // pick warps-per-CTA in [lo, hi] that wastes the fewest lanes for `units` thread slots
 static int pick_warps(int units, int lo, int hi) {
   int nw = (units + 31) / 32, best = lo, best_waste = 1 << 30;
@@ -238,12 +258,23 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
   p.G = (const T*)G; p.out = (T*)out; p.dZ = (T*)dZ; p.dW = (T*)dW; p.dvar = (T*)dvar; p.dls = (T*)dls;
   const int tpb = 32 * pick_warps(M, 1, 4);
   const int nchunk = (M + tpb - 1) / tpb;
-  p.n_items = (long long)nchunk * N * d->C * g.Hout;
-  const size_t smem = fast_smem(p, tpb, BWD);
   if (!BWD) {
     size_t bytes = sizeof(T) * (size_t)M * N * (p.out_per_channel ? d->C : 1);
     CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
   }
+  static const int use_mma = env_choice(BWD ? "CGP_KUF_BWD" : "CGP_KUF_FWD", BWD ? 0 : 1);
+  if constexpr (std::is_same<T, double>::value) if (use_mma) {
+    // float64: FP64 MMA kernels, work items are blocks of kOctBlock patch octets
+    const int nblk = (g.Pc + 8 * kOctBlock - 1) / (8 * kOctBlock);
+    p.n_items = (long long)nchunk * N * d->C * nblk;
+    const size_t smem_m = mma_smem(p, BWD);
+    const long long unit_m = (long long)d->C * nblk;
+#define CALL(PH_, PW_) return launch_fast(kuf_mma_kernel<PH_, PW_, BWD>, p, tpb, smem_m, st, "kuf", unit_m)
+    CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+  }
+  p.n_items = (long long)nchunk * N * d->C * g.Hout;
+  const size_t smem = fast_smem(p, tpb, BWD);
   // Every CTA walks at least one whole (chunk, image) unit's worth of rows, so an output element
   // receives at most two atomic contributions -> the forward result is order-independent (the
   // reference's tests demand bitwise equalities between kernels, testing/test_convkerns.py:112-128).
@@ -265,16 +296,29 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
   // C*P' patches of the image pair with each other (Conv with colour_channels > 1)
   p.ndom = (mode == 2 || p.out_per_channel) ? d->C : 1;
   const int ppd = d->C / p.ndom, Pd = ppd * g.Pc, Hd = ppd * g.Hout;
-  const int tpb = 32 * pick_warps(Pd, 3, 8);
+  static const int use_mma = env_choice(BWD ? "CGP_KDIAG_BWD" : "CGP_KDIAG_FWD", 0);
+  static const int max_warps = env_choice("CGP_KDIAG_WARPS", 8);
+  const bool mma_path = std::is_same<T, double>::value && use_mma;
+  const int tpb = 32 * pick_warps(Pd, std::min(3, max_warps), max_warps);
   const int nchunk = (Pd + tpb - 1) / tpb;
-  const int maxspan = (31 + g.Wout - 1) / g.Wout;
-  p.S = std::min(Hd, Hd / 2 + 1 + maxspan);
-  p.n_items = (long long)N * p.ndom * nchunk * p.S;
-  const size_t smem = fast_smem(p, tpb, BWD);
   if (!BWD) {
     size_t bytes = sizeof(T) * (size_t)N * (p.out_per_channel ? d->C : 1);
     CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
   }
+  if constexpr (std::is_same<T, double>::value) if (mma_path) {
+    const int Lsweep = std::min(Pd, Pd / 2 + 32);
+    const int noct = (Lsweep + 7) / 8;
+    p.S = (noct + kOctBlock - 1) / kOctBlock;
+    p.n_items = (long long)N * p.ndom * nchunk * p.S;
+    const size_t smem_m = mma_smem(p, BWD);
+#define CALL(PH_, PW_) return launch_fast(kdiag_mma_kernel<PH_, PW_, BWD>, p, tpb, smem_m, st, "kdiag")
+    CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+  }
+  const int maxspan = (31 + g.Wout - 1) / g.Wout;
+  p.S = std::min(Hd, Hd / 2 + 1 + maxspan);
+  p.n_items = (long long)N * p.ndom * nchunk * p.S;
+  const size_t smem = fast_smem(p, tpb, BWD);
 #define CALL(PH_, PW_) return launch_fast(kdiag_fast_kernel<T, PH_, PW_, BWD>, p, tpb, smem, st, "kdiag")
   CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL

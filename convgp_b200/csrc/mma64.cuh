@@ -1,0 +1,524 @@
+// float64 hot kernels on the warp-level FP64 MMA (mma.sync.m8n8k4.f64, SASS DMMA).
+//
+// Why: on B200 the scalar DFMA only reaches the FP64 pipe's rate when an instruction brings at
+// most two new 64-bit register operands (probe kinds 9/10: 11.5 T FMA/s with three distinct
+// operands vs 16.8 T/s peak); the patch-vs-reference contraction is exactly the three-operand
+// case.  The 8x8x4 MMA does 8 FMAs per lane for four operand registers and measures 18.4 T FMA/s
+// on the same pipe (probe kind 4) -- so the contraction, and in the backward pass the second
+// contraction dZ += coef^T X, are issued as DMMA tiles, flash-attention style:
+//
+//   S = ref . patch^T   (GEMM1, K = D padded to 4)  ->  k = exp(S + e_ref + e_patch) in the C
+//   fragment registers  ->  fwd: weighted row sums;  bwd: coef = G w k, then GEMM2
+//   dRef += coef . patch (K = 8 patches per octet), the C->A fragment change done with quad shuffles.
+//
+// A warp owns 32 reference vectors (4 row tiles of 8: inducing patches for Kuf, own image patches
+// for Kdiag) whose A fragments stay in registers; it walks the patches of the staged image in
+// octets (8 consecutive patch indices), gathering B fragments straight from the de-interleaved
+// shared-memory image -- patches are never materialised.  Fragment layouts (PTX ISA, m8n8k4 .f64):
+//   A[row = lane>>2][k = lane&3]   B[k = lane&3][col = lane>>2]   C[row = lane>>2][col = 2*(lane&3) + {0,1}]
+#pragma once
+#include "fast.cuh"
+
+namespace cgp {
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double quad_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+// sum over the 8 lanes that share lane&3 (the rows of a C fragment column pair)
+__device__ __forceinline__ double rows_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+constexpr int kOctBlock = 3;  // octets per work item
+
+template <int PH, int PW>
+struct MmaGeom {
+  static constexpr int D = PH * PW;
+  static constexpr int KS = (D + 3) / 4;  // GEMM1 k-steps
+  static constexpr int DT = (D + 7) / 8;  // GEMM2 column tiles
+};
+
+// offset of patch element d inside the plane, relative to the patch origin (0 for padding dims)
+template <int PH, int PW>
+__device__ __forceinline__ int elem_off(int d, int Wd) {
+  return d < PH * PW ? (d / PW) * Wd + (d % PW) : 0;
+}
+
+// =====================================================================================
+// Kuf forward / backward (float64, DMMA)
+// =====================================================================================
+template <int PH, int PW, bool BWD>
+__global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastParams<double> p) {
+  using T = double;
+  using MG = MmaGeom<PH, PW>;
+  constexpr int D = MG::D, KS = MG::KS, DT = MG::DT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tbl = reinterpret_cast<T*>(smem_raw);
+  T* img = tbl + Math<T>::kTableDoubles;
+  T* e = img + p.C * p.H * p.Wd;
+  const int nW = p.w_per_plane ? p.C * p.Pc : p.Pc;
+  T* w = e + p.C * p.Pc;
+  T* dWacc = w + nW;
+  T* red = dWacc + (BWD ? nW : 0);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const bool do_dw = BWD && p.dW != nullptr;
+  Math<T>::init_table(tbl);
+  for (int i = tid; i < nW; i += blockDim.x) {
+    w[i] = p.Wt ? p.Wt[i] : T(1);
+    if (BWD) dWacc[i] = T(0);
+  }
+  __syncthreads();
+
+  int off1[KS];
+#pragma unroll
+  for (int s = 0; s < KS; ++s) off1[s] = elem_off<PH, PW>(4 * s + lc, p.Wd);
+  int off2[BWD ? DT : 1];
+  if constexpr (BWD) {
+#pragma unroll
+    for (int dt = 0; dt < DT; ++dt) off2[dt] = elem_off<PH, PW>(8 * dt + lr, p.Wd);
+  }
+
+  const long long lo = p.n_items * blockIdx.x / gridDim.x;
+  const long long hi = p.n_items * (blockIdx.x + 1) / gridDim.x;
+  const int nblk = (p.Pc + 8 * kOctBlock - 1) / (8 * kOctBlock);
+
+  T a[4][KS];              // A fragments of the 4 row tiles (scaled inducing patches)
+  T em[4];                 // e_ref of row (8t + lr)
+  T acc[4];                // fwd: sigma^2 * sum_p w_p k   (partial over this lane's columns)
+  T dz[BWD ? 4 : 1][BWD ? DT : 1][2];
+  T s0[4], s2[4], Gm[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) acc[t] = s0[t] = s2[t] = Gm[t] = em[t] = T(0);
+  int cur_zkey = -1, cur_img = -1, cur_okey = -1;
+  int zc = 0, zchunk = 0, on = 0, oc = 0, ochunk = 0;
+  T sig2 = T(0), inv_l2 = T(0), lsg = T(1);
+
+  auto row_m = [&](int chunk, int t) { return chunk * (int)blockDim.x + warp * 32 + 8 * t + lr; };
+
+  auto flush_out = [&]() {
+    if constexpr (!BWD) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const T v = quad_sum(acc[t]);
+        const int m = row_m(ochunk, t);
+        if (lc == 0 && m < p.M) {
+          size_t o = p.out_per_channel ? ((size_t)m * p.N + on) * p.C + oc : (size_t)m * p.N + on;
+          atomicAdd(p.out + o, v / p.Pn);
+        }
+        acc[t] = T(0);
+      }
+    }
+  };
+  auto flush_z = [&]() {
+    if constexpr (BWD) {
+      T t0 = T(0), t2 = T(0);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const T s0m = quad_sum(s0[t]);  // total over the row's patches, in all 4 lanes of the quad
+        t0 += s0[t];
+        t2 += s2[t];
+        const int m = row_m(zchunk, t);
+        if (m < p.M && p.dZ) {
+          const T* zrow = p.Z + (size_t)m * p.Dtot + zc * p.zplane;
+          T* drow = p.dZ + (size_t)m * p.Dtot + zc * p.zplane;
+#pragma unroll
+          for (int dt = 0; dt < DT; ++dt)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              const int d = 8 * dt + 2 * lc + x;
+              if (d < D) atomicAdd(drow + d * p.zstride, sig2 * inv_l2 * (dz[t][dt][x] - zrow[d * p.zstride] * s0m));
+            }
+        }
+        s0[t] = s2[t] = T(0);
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) dz[t][dt][0] = dz[t][dt][1] = T(0);
+      }
+      t0 = block_sum(t0, red);
+      t2 = block_sum(t2, red);
+      if (tid == 0) {
+        const int g = p.grp_per_plane ? zc : 0;
+        if (p.dvar) atomicAdd(p.dvar + g, t0);
+        if (p.dls) atomicAdd(p.dls + g, T(-2) * sig2 / lsg * t2);
+      }
+    }
+  };
+
+  for (long long it = lo; it < hi; ++it) {
+    long long tt = it;
+    const int blk = (int)(tt % nblk);
+    tt /= nblk;
+    const int c = (int)(tt % p.C);
+    tt /= p.C;
+    const int n = (int)(tt % p.N);
+    const int chunk = (int)(tt / p.N);
+
+    const int zkey = chunk * p.C + (p.zplane || p.grp_per_plane ? c : 0);
+    const int okey = (chunk * p.N + n) * p.C + (p.out_per_channel ? c : 0);
+    if (okey != cur_okey) {
+      if (cur_okey >= 0) flush_out();
+      cur_okey = okey;
+      on = n;
+      oc = c;
+      ochunk = chunk;
+      if constexpr (BWD) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int m = row_m(chunk, t);
+          size_t o = p.out_per_channel ? ((size_t)m * p.N + n) * p.C + c : (size_t)m * p.N + n;
+          Gm[t] = m < p.M ? p.G[o] / p.Pn : T(0);
+        }
+      }
+    }
+    if (zkey != cur_zkey) {
+      if (cur_zkey >= 0) flush_z();
+      cur_zkey = zkey;
+      zc = c;
+      zchunk = chunk;
+      const int g = p.grp_per_plane ? c : 0;
+      sig2 = p.var[g];
+      lsg = p.ls[g];
+      inv_l2 = T(1) / (lsg * lsg);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int m = row_m(chunk, t);
+        const bool act = m < p.M;
+        const T* zrow = p.Z + (size_t)(act ? m : 0) * p.Dtot + c * p.zplane;
+        T zz = T(0);  // this lane's share of |z_m|^2; the quad covers all dims
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          const int d = 4 * s + lc;
+          const T zv = (act && d < D) ? zrow[d * p.zstride] : T(0);
+          a[t][s] = zv * inv_l2;
+          zz = fma(zv, zv, zz);
+        }
+        em[t] = T(-0.5) * inv_l2 * quad_sum(zz);
+        if constexpr (BWD) {
+#pragma unroll
+          for (int dt = 0; dt < DT; ++dt) dz[t][dt][0] = dz[t][dt][1] = T(0);
+        }
+      }
+    }
+    if (n != cur_img) {
+      __syncthreads();
+      stage_image<T, PH, PW>(p, n, img, e);
+      cur_img = n;
+    }
+
+    const T* plane = img + c * p.H * p.Wd;
+    const T* ep = e + c * p.Pc;
+    const int woff = p.w_per_plane ? c * p.Pc : 0;
+    const T* wp = w + woff;
+#pragma unroll 1
+    for (int ob = 0; ob < kOctBlock; ++ob) {
+      const int p0 = (blk * kOctBlock + ob) * 8;
+      if (p0 >= p.Pc) break;
+      // ---- GEMM1: S[row][patch] = ref . patch
+      const int pB = min(p0 + lr, p.Pc - 1);
+      const T* bB = plane + (pB / p.Wout) * p.Wd + (pB % p.Wout);
+      const int pC0 = p0 + 2 * lc;
+      const bool v0 = pC0 < p.Pc, v1 = pC0 + 1 < p.Pc;
+      const T e0 = ep[min(pC0, p.Pc - 1)], e1 = ep[min(pC0 + 1, p.Pc - 1)];
+      T cfr[4][2];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        cfr[t][0] = em[t] + e0;
+        cfr[t][1] = em[t] + e1;
+      }
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const T b = bB[off1[s]];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dmma(cfr[t], a[t][s], b);
+      }
+      const T w0 = v0 ? wp[pC0] : T(0), w1 = v1 ? wp[pC0 + 1] : T(0);
+      if constexpr (!BWD) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const T k0 = Math<T>::exp_arg(v0 ? cfr[t][0] : T(0), tbl);
+          const T k1 = Math<T>::exp_arg(v1 ? cfr[t][1] : T(0), tbl);
+          acc[t] = fma(w0 * sig2, k0, acc[t]);
+          acc[t] = fma(w1 * sig2, k1, acc[t]);
+        }
+      } else {
+        T vs0 = T(0), vs1 = T(0);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const T a0 = v0 ? cfr[t][0] : T(0), a1 = v1 ? cfr[t][1] : T(0);
+          const T g0 = Gm[t] * Math<T>::exp_arg(a0, tbl);
+          const T g1 = Gm[t] * Math<T>::exp_arg(a1, tbl);
+          vs0 += g0;
+          vs1 += g1;
+          cfr[t][0] = g0 * w0;  // coef
+          cfr[t][1] = g1 * w1;
+          s0[t] += cfr[t][0] + cfr[t][1];
+          s2[t] = fma(cfr[t][0], a0, s2[t]);
+          s2[t] = fma(cfr[t][1], a1, s2[t]);
+        }
+        if (do_dw) {
+          vs0 = rows_sum(vs0);
+          vs1 = rows_sum(vs1);
+          if (lr == 0) {
+            if (v0) atomicAdd(dWacc + woff + pC0, vs0 * sig2);
+            if (v1) atomicAdd(dWacc + woff + pC0 + 1, vs1 * sig2);
+          }
+        }
+        // ---- GEMM2: dz[row][d] += coef[row][patch] * X[patch][d]
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int pK = min(p0 + 4 * h + lc, p.Pc - 1);
+          const T* bK = plane + (pK / p.Wout) * p.Wd + (pK % p.Wout);
+          T b2[DT];
+#pragma unroll
+          for (int dt = 0; dt < DT; ++dt) b2[dt] = bK[off2[dt]];
+          const int src = (lane & ~3) | (2 * h + (lc >> 1));
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const T x0 = __shfl_sync(0xffffffffu, cfr[t][0], src);
+            const T x1 = __shfl_sync(0xffffffffu, cfr[t][1], src);
+            const T a2 = (lc & 1) ? x1 : x0;
+#pragma unroll
+            for (int dt = 0; dt < DT; ++dt) dmma(dz[t][dt], a2, b2[dt]);
+          }
+        }
+      }
+    }
+  }
+  if (cur_okey >= 0) flush_out();
+  if (cur_zkey >= 0) flush_z();
+  if (do_dw) {
+    __syncthreads();
+    for (int i = tid; i < nW; i += blockDim.x) {
+      T v = dWacc[i];
+      if (v != T(0)) atomicAdd(p.dW + i, v);
+    }
+  }
+}
+
+// =====================================================================================
+// Kdiag forward / backward (float64, DMMA).  Row tiles = the warp's 32 own patches of a pairing
+// domain (see kdiag_fast_kernel); columns = patches p' swept over the cyclic half range
+// delta = (p' - p) mod Pd in [0, Pd/2]: weight 1 for delta == 0 and delta == Pd/2 (visited from
+// both sides), 2 otherwise, 0 beyond -- every unordered pair once, equal load for every warp.
+// =====================================================================================
+template <int PH, int PW, bool BWD>
+__global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<double> p) {
+  using T = double;
+  using MG = MmaGeom<PH, PW>;
+  constexpr int D = MG::D, KS = MG::KS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tbl = reinterpret_cast<T*>(smem_raw);
+  T* img = tbl + Math<T>::kTableDoubles;
+  T* e = img + p.C * p.H * p.Wd;
+  const int nW = p.w_per_plane ? p.C * p.Pc : p.Pc;
+  T* w = e + p.C * p.Pc;
+  T* dWacc = w + nW;
+  T* red = dWacc + (BWD ? nW : 0);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const bool do_dw = BWD && p.dW != nullptr;
+  Math<T>::init_table(tbl);
+  for (int i = tid; i < nW; i += blockDim.x) {
+    w[i] = p.Wt ? p.Wt[i] : T(1);
+    if (BWD) dWacc[i] = T(0);
+  }
+  __syncthreads();
+
+  int off1[KS];
+#pragma unroll
+  for (int s = 0; s < KS; ++s) off1[s] = elem_off<PH, PW>(4 * s + lc, p.Wd);
+
+  const long long lo = p.n_items * blockIdx.x / gridDim.x;
+  const long long hi = p.n_items * (blockIdx.x + 1) / gridDim.x;
+  const int ndom = p.ndom, ppd = p.C / ndom, Pd = ppd * p.Pc;
+  const int nchunk = (Pd + blockDim.x - 1) / blockDim.x;
+  const int half = Pd / 2;
+  const bool even = (Pd & 1) == 0;
+  const int Lsweep = min(Pd, half + 32);  // visit indices [0, Lsweep) starting at the warp's first patch
+  const T P2 = p.Pn * p.Pn;
+
+  // patch index inside the domain -> offset of its origin in the staged image (planes stacked)
+  auto origin = [&](int cb, int pd) {
+    const int cp = pd / p.Pc, pp = pd - cp * p.Pc;
+    return (cb + cp) * p.H * p.Wd + (pp / p.Wout) * p.Wd + (pp % p.Wout);
+  };
+
+  T a[4][KS], em[4], wown[4];
+  int own[4];
+  T acc[4], acc2[4], dwown[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    acc[t] = acc2[t] = dwown[t] = em[t] = wown[t] = T(0);
+    own[t] = 0;
+  }
+  int cur_key = -1, cur_img = -1, kn = 0, kdm = 0;
+  T sig2 = T(0), lsg = T(1);
+
+  auto flush = [&]() {
+    const int g = p.grp_per_plane ? kdm : 0;
+    const size_t o = p.out_per_channel ? (size_t)kn * p.C + kdm : (size_t)kn;
+    const int cb = (ndom == 1) ? 0 : kdm;
+    T v = T(0), v2 = T(0);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      v = fma(wown[t], acc[t], v);  // wown is 0 for inactive rows
+      v2 = fma(wown[t], acc2[t], v2);
+    }
+    if constexpr (!BWD) {
+      v = block_sum(v, red);
+      if (tid == 0) atomicAdd(p.out + o, v * sig2 / P2);
+    } else {
+      const T gn = p.G[o] / P2;
+      v = block_sum(v, red);
+      v2 = block_sum(v2, red);
+      if (tid == 0) {
+        if (p.dvar) atomicAdd(p.dvar + g, gn * v);
+        if (p.dls) atomicAdd(p.dls + g, T(-2) * sig2 / lsg * gn * v2);
+      }
+      if (do_dw) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const T d = quad_sum(dwown[t]);
+          if (lc == 0 && own[t] < Pd)
+            atomicAdd(dWacc + (p.w_per_plane ? cb * p.Pc : 0) + own[t], T(2) * sig2 * gn * d);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[t] = acc2[t] = dwown[t] = T(0);
+  };
+
+  for (long long it = lo; it < hi; ++it) {
+    long long tt = it;
+    const int blk = (int)(tt % p.S);
+    tt /= p.S;
+    const int j = (int)(tt % nchunk);
+    tt /= nchunk;
+    const int dm = (int)(tt % ndom);
+    const int n = (int)(tt / ndom);
+    const int cb = (ndom == 1) ? 0 : dm;
+    const int key = (n * ndom + dm) * nchunk + j;
+    const int wbase = j * blockDim.x + warp * 32;  // first own patch of this warp
+    if (key != cur_key) {
+      if (cur_key >= 0) flush();
+      if (n != cur_img) {
+        __syncthreads();
+        stage_image<T, PH, PW>(p, n, img, e);
+        cur_img = n;
+      }
+      cur_key = key;
+      kn = n;
+      kdm = dm;
+      const int g = p.grp_per_plane ? dm : 0;
+      sig2 = p.var[g];
+      lsg = p.ls[g];
+      const T sc = T(1) / (lsg * lsg);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        own[t] = wbase + 8 * t + lr;
+        const bool act = own[t] < Pd;
+        const T* base = img + origin(cb, act ? own[t] : 0);
+#pragma unroll
+        for (int s = 0; s < KS; ++s) a[t][s] = (act && 4 * s + lc < D) ? base[off1[s]] * sc : T(0);
+        em[t] = act ? e[cb * p.Pc + own[t]] : T(0);
+        wown[t] = act ? w[(p.w_per_plane ? cb * p.Pc : 0) + own[t]] : T(0);
+      }
+    }
+    if (wbase >= Pd) continue;  // warp without own patches
+    const T* ep = e + cb * p.Pc;
+    const int woff = p.w_per_plane ? cb * p.Pc : 0;
+    const T* wp = w + woff;
+    T gs = T(0);
+    if constexpr (BWD) {
+      const size_t o = p.out_per_channel ? (size_t)n * p.C + dm : (size_t)n;
+      gs = T(2) * sig2 * p.G[o] / P2;
+    }
+#pragma unroll 1
+    for (int ob = 0; ob < kOctBlock; ++ob) {
+      const int v0i = (blk * kOctBlock + ob) * 8;  // visit index of the octet's first column
+      if (v0i >= Lsweep) break;
+      // columns: B fragment lane lr, C fragment lanes 2*lc + {0,1}
+      const int viB = min(v0i + lr, Lsweep - 1);
+      int pB = wbase + viB;
+      pB -= pB >= Pd ? Pd : 0;
+      const T* bB = img + origin(cb, pB);
+      const int vi0 = v0i + 2 * lc, vi1 = vi0 + 1;
+      const bool c0 = vi0 < Lsweep, c1 = vi1 < Lsweep;
+      int q0 = wbase + min(vi0, Lsweep - 1), q1 = wbase + min(vi1, Lsweep - 1);
+      q0 -= q0 >= Pd ? Pd : 0;
+      q1 -= q1 >= Pd ? Pd : 0;
+      const T e0 = ep[q0], e1 = ep[q1];
+      T cfr[4][2];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        cfr[t][0] = em[t] + e0;
+        cfr[t][1] = em[t] + e1;
+      }
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const T b = bB[off1[s]];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dmma(cfr[t], a[t][s], b);
+      }
+      const T w0 = c0 ? wp[q0] : T(0), w1 = c1 ? wp[q1] : T(0);
+      T sc0 = T(0), sc1 = T(0);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        // pair weights from the cyclic distance (own -> column)
+        int d0 = q0 - own[t], d1 = q1 - own[t];
+        d0 += d0 < 0 ? Pd : 0;
+        d1 += d1 < 0 ? Pd : 0;
+        int wt0 = d0 == 0 ? 1 : (d0 < half || (!even && d0 == half)) ? 2 : (even && d0 == half) ? 1 : 0;
+        int wt1 = d1 == 0 ? 1 : (d1 < half || (!even && d1 == half)) ? 2 : (even && d1 == half) ? 1 : 0;
+        if (!c0 || own[t] >= Pd) wt0 = 0;
+        if (!c1 || own[t] >= Pd) wt1 = 0;
+        const T a0 = wt0 ? cfr[t][0] : T(0), a1 = wt1 ? cfr[t][1] : T(0);
+        const T k0 = Math<T>::exp_arg(a0, tbl), k1 = Math<T>::exp_arg(a1, tbl);
+        const T wk0 = w0 * k0, wk1 = w1 * k1;
+        acc[t] = fma((T)wt0, wk0, acc[t]);
+        acc[t] = fma((T)wt1, wk1, acc[t]);
+        if constexpr (BWD) {
+          acc2[t] = fma((T)wt0 * wk0, a0, acc2[t]);
+          acc2[t] = fma((T)wt1 * wk1, a1, acc2[t]);
+          dwown[t] += (wt0 ? wk0 : T(0)) + (wt1 ? wk1 : T(0));
+          sc0 = fma(wt0 == 2 ? wown[t] : T(0), k0, sc0);
+          sc1 = fma(wt1 == 2 ? wown[t] : T(0), k1, sc1);
+        }
+      }
+      if constexpr (BWD) {
+        if (do_dw) {
+          sc0 = rows_sum(sc0);
+          sc1 = rows_sum(sc1);
+          if (lr == 0) {
+            if (c0) atomicAdd(dWacc + woff + q0, sc0 * gs);
+            if (c1) atomicAdd(dWacc + woff + q1, sc1 * gs);
+          }
+        }
+      }
+    }
+  }
+  if (cur_key >= 0) flush();
+  if (do_dw) {
+    __syncthreads();
+    for (int i = tid; i < nW; i += blockDim.x) {
+      T v = dWacc[i];
+      if (v != T(0)) atomicAdd(p.dW + i, v);
+    }
+  }
+}
+
+}  // namespace cgp

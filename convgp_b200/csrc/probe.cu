@@ -15,7 +15,25 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, double* sink, dou
     Math<double>::init_table(tbl);
     __syncthreads();
   }
-  if (KIND == 9 || KIND == 10) {  // FP64 FMA with three distinct register operands (9) / one shared multiplier (10)
+  if (KIND == 11 || KIND == 12 || KIND == 13) {  // DMMA with 1 / 2 / 4 dependent chains, one warp per sub-partition
+    constexpr int NC = KIND == 11 ? 1 : (KIND == 12 ? 2 : 4);
+    double acc[NC][2], a = seed + tid * 1e-6, b = 1.0 + seed * 1e-9;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc[i][0] = acc[i][1] = i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int r = 0; r < 8 / NC; ++r)
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][0]), "+d"(acc[i][1])
+                       : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) s += acc[i][0] + acc[i][1];
+    if (s == 12345.678) sink[0] = s;
+  } else if (KIND == 9 || KIND == 10) {  // FP64 FMA with three distinct register operands (9) / one shared multiplier (10)
     double a[kChains], b[kChains], c[kChains];
 #pragma unroll
     for (int i = 0; i < kChains; ++i) {
@@ -141,7 +159,8 @@ template <int KIND>
 static int run_probe(double ops_per_thread_iter, double* result) {
   double* sink = nullptr;
   CGP_CUDA_CHECK(cudaMalloc(&sink, sizeof(double)));
-  const int blocks = KIND == 6 ? num_sms() : num_sms() * 8, threads = KIND == 6 ? 128 : 256;
+  constexpr bool kOneWarp = KIND == 6 || KIND == 11 || KIND == 12 || KIND == 13;
+  const int blocks = kOneWarp ? num_sms() : num_sms() * 8, threads = kOneWarp ? 128 : 256;
   const int iters = (KIND == 3) ? 512 : (KIND >= 4 ? 1024 : 4096);
   cudaEvent_t e0, e1;
   CGP_CUDA_CHECK(cudaEventCreate(&e0));
@@ -189,6 +208,10 @@ extern "C" int cgp_peak_probe(int32_t kind, double* ops_per_s) {
     // register-file read bandwidth: three distinct 64-bit operands per FMA (9), one of them shared (10)
     case 9: return run_probe<9>(kChains, ops_per_s);
     case 10: return run_probe<10>(kChains, ops_per_s);
+    // DMMA issue latency: 8 mma per iteration in 1 / 2 / 4 dependent chains, one warp per sub-partition
+    case 11: return run_probe<11>(64.0, ops_per_s);
+    case 12: return run_probe<12>(64.0, ops_per_s);
+    case 13: return run_probe<13>(64.0, ops_per_s);
     default:
       set_error("unknown probe kind %d", kind);
       return CGP_ERR_BAD_DESC;
