@@ -1,0 +1,21 @@
+"""Both float64 kernel families (FP64-MMA and scalar-FMA) must pass parity whatever the library's
+default selection is: re-run the f64 parity + golden tests in subprocesses with the selection forced."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("family", ["mma", "fma"])
+def test_forced_kernel_family(family):
+    env = dict(os.environ)
+    for k in ("CGP_KUF_FWD", "CGP_KUF_BWD", "CGP_KDIAG_FWD", "CGP_KDIAG_BWD"):
+        env[k] = family
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-k", "f64", "tests/test_gpu_parity.py",
+                        "tests/test_golden.py", "tests/test_gpu_identities.py", "-p", "no:cacheprovider"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
