@@ -5,3 +5,8 @@ and ``convkernels``) and adds the kernel/model modules the reference scripts pul
 from .settings import settings  # noqa: F401
 from . import convkernels  # noqa: F401
 from . import kernels  # noqa: F401
+from . import likelihoods  # noqa: F401,E402
+from . import misvgp  # noqa: F401,E402
+from . import svgp  # noqa: F401,E402
+from . import svsumgp  # noqa: F401,E402
+from . import svconvgp  # noqa: F401,E402

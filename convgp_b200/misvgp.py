@@ -56,3 +56,40 @@ def conditional(Xnew, X, Kdiag, Kmn, Kmm, f, full_cov=False, q_sqrt=None, whiten
             raise ValueError("Bad dimension for q_sqrt: %s" % str(q_sqrt.dim()))
         fvar = fvar + (LTA * LTA).sum(1)  # :162
     return fmean, fvar.T  # :163-165
+
+
+def _svgp_base():
+    from .svgp import SVGP
+    return SVGP
+
+
+class MultiOutputInducingSVGP(_svgp_base()):
+    """misvgp.py:168-210: every inducing patch carries ``kern.inducing_outputs`` (= C) inducing
+    outputs; the prediction sums the C per-channel conditionals, which share one Kmm / Cholesky.
+    (The reference re-emits Kdiag / Kmn / Kmm per channel and leaves a debug ``tf.Print`` in the
+    graph, misvgp.py:194-196,209; both are dropped -- values are identical.)"""
+
+    def __init__(self, X, Y, kern, likelihood, Z, mean_function=None, num_latent=None, q_diag=False, whiten=True,
+                 minibatch_size=None):
+        _svgp_base().__init__(self, X, Y, kern, likelihood, Z, mean_function, num_latent, q_diag, whiten,
+                              minibatch_size)
+        from .param import LowerTriangular
+        M, L, C = self.num_inducing, self.num_latent, kern.inducing_outputs
+        self.q_mu = Param(np.zeros((M, L * C)))
+        q_sqrt = np.array([np.eye(M) for _ in range(L * C)]).swapaxes(0, 2).reshape(M, M, C * L)
+        self.q_sqrt = Param(q_sqrt, LowerTriangular(M, C * L))
+
+    def build_predict(self, Xnew, full_cov=False):
+        from .settings import settings
+        M, L, C = self.num_inducing, self.num_latent, self.kern.inducing_outputs
+        q_mu = self.q_mu().reshape(M, L, C)
+        q_sqrt = self.q_sqrt().reshape(M, M, L, C)
+        Z = self.Z()
+        Kdiag, Kmn = self.kern.Kdiag(Xnew), self.kern.Kzx(Z, Xnew)
+        Kmm = self.kern.Kzz(Z) + torch.eye(M, dtype=Z.dtype, device=Z.device) * settings.jitter_level
+        mu, var = 0, 0
+        for i in range(C):
+            fmu, fvar = conditional(Xnew, Z, Kdiag[:, i], Kmn[:, :, i], Kmm, q_mu[:, :, i],
+                                    q_sqrt=q_sqrt[:, :, :, i], full_cov=full_cov, whiten=self.whiten)
+            mu, var = mu + fmu, var + fvar
+        return mu, var

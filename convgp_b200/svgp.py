@@ -1,0 +1,175 @@
+"""Sparse variational GP with inter-domain inducing patches: the model the reference scripts build
+(``GPflow.svgp.SVGP`` of the GPflow-inter-domain fork, mirrored in-tree by svconvgp.py:91-104 for
+the ELBO and misvgp.py:83-165 for the conditional).  Same constructor, parameters (Z, q_mu, q_sqrt)
+and methods (build_prior_KL, build_predict, build_likelihood, predict_y, compute_log_likelihood,
+_objective, get_free_state / set_state).  Kernel matrices come from the CUDA hot path; Cholesky /
+triangular solves / the batched L^T A product are library calls (cuSOLVER / cuBLAS through torch)."""
+import numpy as np
+import torch
+
+from . import parallel
+from .kernels import as_tensor
+from .misvgp import conditional
+from .param import LowerTriangular, Param, Parameterized, Positive
+from .settings import settings
+
+
+def gauss_kl_white(q_mu, q_sqrt):
+    """KL[N(q_mu, q_sqrt q_sqrt^T) || N(0, I)] summed over latents (GPflow 0.x gauss_kl_white)."""
+    KL = 0.5 * (q_mu ** 2).sum() - 0.5 * q_mu.numel()
+    L = torch.tril(q_sqrt.permute(2, 0, 1))
+    KL = KL - 0.5 * torch.log(torch.diagonal(L, dim1=1, dim2=2) ** 2).sum()
+    return KL + 0.5 * (L ** 2).sum()
+
+
+def gauss_kl_white_diag(q_mu, q_sqrt):
+    KL = 0.5 * (q_mu ** 2).sum() - 0.5 * q_mu.numel()
+    return KL - 0.5 * torch.log(q_sqrt ** 2).sum() + 0.5 * (q_sqrt ** 2).sum()
+
+
+def gauss_kl(q_mu, q_sqrt, K):
+    """KL[N(q_mu, S) || N(0, K)] summed over latents (GPflow 0.x gauss_kl / gauss_kl_diag)."""
+    M, L_ = q_mu.shape
+    Lk = torch.linalg.cholesky(K)
+    alpha = torch.linalg.solve_triangular(Lk, q_mu, upper=False)
+    KL = 0.5 * (alpha ** 2).sum() + L_ * torch.log(torch.diagonal(Lk)).sum() - 0.5 * M * L_
+    if q_sqrt.dim() == 2:
+        KL = KL - 0.5 * torch.log(q_sqrt ** 2).sum()
+        Kinv = torch.cholesky_inverse(Lk)
+        return KL + 0.5 * (torch.diagonal(Kinv)[:, None] * q_sqrt ** 2).sum()
+    Lq = torch.tril(q_sqrt.permute(2, 0, 1))
+    KL = KL - 0.5 * torch.log(torch.diagonal(Lq, dim1=1, dim2=2) ** 2).sum()
+    LiLq = torch.linalg.solve_triangular(Lk[None].expand(L_, -1, -1), Lq, upper=False)
+    return KL + 0.5 * (LiLq ** 2).sum()
+
+
+class Model(Parameterized):
+    """Objective plumbing shared by the SVGP family."""
+
+    def build_likelihood(self):
+        raise NotImplementedError
+
+    def build_prior(self):
+        return 0.0
+
+    def compute_log_likelihood(self):
+        with torch.no_grad():
+            return float(self.build_likelihood())
+
+    def _objective(self, x):
+        """(-ELBO, gradient) at free state x, float64 NumPy like GPflow's (opt_tools/helpers.py:108-117).
+        With an initialised process group the data term is this rank's shard and the packed
+        [f | g] buffer is summed across ranks."""
+        self.set_state(x)
+        ps = self.free_params()
+        for p in ps:
+            p.free.grad = None
+        f = -(self.build_likelihood() + self.build_prior())
+        f.backward()
+        flat = torch.cat([f.detach().reshape(1)] + [
+            (p.free.grad if p.free.grad is not None else torch.zeros_like(p.free)).reshape(-1) for p in ps])
+        parallel.allreduce_sum_(flat)
+        out = flat.double().cpu().numpy()
+        return out[0], out[1:]
+
+    def optimize(self, method="L-BFGS-B", maxiter=1000, callback=None, lr=1e-3, **kw):
+        """Drive the objective with scipy (method string) or a torch optimiser class / 'adam'."""
+        if isinstance(method, str) and method.lower() != "adam":
+            from scipy.optimize import minimize
+            res = minimize(self._objective, self.get_free_state(), jac=True, method=method, callback=callback,
+                           options=dict(maxiter=maxiter, **kw))
+            self.set_state(res.x)
+            return res
+        opt_cls = torch.optim.Adam if isinstance(method, str) else method
+        opt = opt_cls([p.free for p in self.free_params()], lr=lr)
+        for _ in range(maxiter):
+            opt.zero_grad()
+            f = -(self.build_likelihood() + self.build_prior())
+            f.backward()
+            opt.step()
+            if callback is not None:
+                callback(self.get_free_state())
+        return None
+
+
+class SVGP(Model):
+    def __init__(self, X, Y, kern, likelihood, Z, mean_function=None, num_latent=None, q_diag=False, whiten=True,
+                 minibatch_size=None):
+        self.X = as_tensor(X)
+        self.Y = as_tensor(Y)
+        self.kern, self.likelihood = kern, likelihood
+        self.mean_function = mean_function
+        self.q_diag, self.whiten = q_diag, whiten
+        self.num_data = self.X.shape[0]
+        self.minibatch_size = minibatch_size
+        self._rng = np.random.RandomState(0)
+        self.num_latent = num_latent or self.Y.shape[1]
+        if Z is not None:
+            self.Z = Param(Z)
+            self.num_inducing = self.Z.shape[0]
+            self._init_variational(self.num_inducing, self.num_latent)
+
+    def _init_variational(self, M, L):
+        self.q_mu = Param(np.zeros((M, L)))
+        if self.q_diag:
+            self.q_sqrt = Param(np.ones((M, L)), Positive())
+        else:
+            self.q_sqrt = Param(np.array([np.eye(M) for _ in range(L)]).swapaxes(0, 2), LowerTriangular(M, L))
+
+    # ------------------------------------------------------------------ minibatching
+    def _minibatch(self):
+        if self.minibatch_size is None or self.minibatch_size >= self.num_data:
+            return self.X, self.Y
+        idx = torch.as_tensor(self._rng.permutation(self.num_data)[:self.minibatch_size], device=self.X.device)
+        return self.X[idx], self.Y[idx]
+
+    # ------------------------------------------------------------------ model terms
+    def build_prior_KL(self):
+        q_mu, q_sqrt = self.q_mu(), self.q_sqrt()
+        if self.whiten:
+            return gauss_kl_white_diag(q_mu, q_sqrt) if self.q_diag else gauss_kl_white(q_mu, q_sqrt)
+        Z = self.Z()
+        K = self.kern.Kzz(Z) + torch.eye(Z.shape[0], dtype=Z.dtype, device=Z.device) * settings.jitter_level
+        return gauss_kl(q_mu, q_sqrt, K)
+
+    def build_predict(self, Xnew, full_cov=False):
+        Z = self.Z()
+        Kmm = self.kern.Kzz(Z) + torch.eye(Z.shape[0], dtype=Z.dtype, device=Z.device) * settings.jitter_level
+        mu, var = conditional(Xnew, Z, self.kern.Kdiag(Xnew), self.kern.Kzx(Z, Xnew), Kmm, self.q_mu(),
+                              full_cov=full_cov, q_sqrt=self.q_sqrt(), whiten=self.whiten)
+        if self.mean_function is not None:
+            mu = mu + self.mean_function(Xnew)
+        return mu, var
+
+    def build_likelihood(self):  # svconvgp.py:91-104
+        Xb, Yb = self._minibatch()
+        world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        if world > 1:  # data parallel: this rank's rows; the KL term is counted once (rank 0)
+            Xb, Yb = parallel.shard_rows(Xb, world, rank), parallel.shard_rows(Yb, world, rank)
+        n_batch = self.minibatch_size if (self.minibatch_size and self.minibatch_size < self.num_data) \
+            else self.num_data
+        fmean, fvar = self.build_predict(Xb)
+        var_exp = self.likelihood.variational_expectations(fmean, fvar, Yb)
+        scale = float(self.num_data) / float(n_batch)
+        ll = var_exp.sum() * scale
+        if rank == 0:
+            ll = ll - self.build_prior_KL()
+        return ll
+
+    # ------------------------------------------------------------------ prediction
+    def predict_f(self, Xnew):
+        with torch.no_grad():
+            mu, var = self.build_predict(as_tensor(Xnew))
+        return mu.cpu().numpy(), var.cpu().numpy()
+
+    def predict_y(self, Xnew):
+        with torch.no_grad():
+            mu, var = self.build_predict(as_tensor(Xnew))
+            m, v = self.likelihood.predict_mean_and_var(mu, var)
+        return m.cpu().numpy(), v.cpu().numpy()
+
+    def predict_density(self, Xnew, Ynew):
+        with torch.no_grad():
+            mu, var = self.build_predict(as_tensor(Xnew))
+            return self.likelihood.predict_density(mu, var, as_tensor(Ynew)).cpu().numpy()
