@@ -172,7 +172,7 @@ template <typename T>
 static size_t mma_smem(const FastParams<T>& p, bool bwd) {
   size_t nW = p.w_per_plane ? (size_t)p.C * p.Pc : (size_t)p.Pc;
   size_t n = (size_t)p.C * p.H * p.Wd + (size_t)p.C * p.Pc + nW + (bwd ? nW : 0) + 32 + Math<T>::kTableDoubles;
-  return n * sizeof(T);
+  return n * sizeof(T) + ((size_t)p.C * p.Pc * sizeof(int) + 15) / 16 * 16;  // + patch-origin table
 }
 
 // pick warps-per-CTA in [lo, hi] that wastes the fewest lanes for `units` thread slots
@@ -265,11 +265,17 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
   static const int use_mma = env_choice(BWD ? "CGP_KUF_BWD" : "CGP_KUF_FWD", BWD ? 0 : 1);
   if constexpr (std::is_same<T, double>::value) if (use_mma) {
     // float64: FP64 MMA kernels, work items are blocks of kOctBlock patch octets
+    static const int nt = env_choice("CGP_KUF_TILES", 4);  // row tiles per warp (2 or 4)
     const int nblk = (g.Pc + 8 * kOctBlock - 1) / (8 * kOctBlock);
-    p.n_items = (long long)nchunk * N * d->C * nblk;
+    const int tpb_m = 32 * pick_warps((M + (8 * nt) - 1) / (8 * nt) * 32, 1, 4);  // a warp covers 8*nt rows
+    const int rows_cta = (tpb_m / 32) * 8 * nt;
+    const int nchunk_m = (M + rows_cta - 1) / rows_cta;
+    p.n_items = (long long)nchunk_m * N * d->C * nblk;
     const size_t smem_m = mma_smem(p, BWD);
     const long long unit_m = (long long)d->C * nblk;
-#define CALL(PH_, PW_) return launch_fast(kuf_mma_kernel<PH_, PW_, BWD>, p, tpb, smem_m, st, "kuf", unit_m)
+#define CALL(PH_, PW_)                                                                                   \
+  if (nt == 4) return launch_fast(kuf_mma_kernel<PH_, PW_, BWD, 4>, p, tpb_m, smem_m, st, "kuf", unit_m); \
+  return launch_fast(kuf_mma_kernel<PH_, PW_, BWD, 2>, p, tpb_m, smem_m, st, "kuf", unit_m)
     CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL
   }

@@ -59,8 +59,9 @@ __device__ __forceinline__ int elem_off(int d, int Wd) {
 // =====================================================================================
 // Kuf forward / backward (float64, DMMA)
 // =====================================================================================
-template <int PH, int PW, bool BWD>
-__global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastParams<double> p) {
+// NT = row tiles (of 8 inducing patches) per warp: fewer tiles -> fewer registers -> more resident warps.
+template <int PH, int PW, bool BWD, int NT>
+__global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 4)) kuf_mma_kernel(const FastParams<double> p) {
   using T = double;
   using MG = MmaGeom<PH, PW>;
   constexpr int D = MG::D, KS = MG::KS, DT = MG::DT;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastPar
   T* w = e + p.C * p.Pc;
   T* dWacc = w + nW;
   T* red = dWacc + (BWD ? nW : 0);
+  int* org = reinterpret_cast<int*>(red + 32);  // org[c*Pc + p]: offset of patch p's origin in the staged image
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
@@ -80,6 +82,10 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastPar
   for (int i = tid; i < nW; i += blockDim.x) {
     w[i] = p.Wt ? p.Wt[i] : T(1);
     if (BWD) dWacc[i] = T(0);
+  }
+  for (int i = tid; i < p.C * p.Pc; i += blockDim.x) {
+    const int cp = i / p.Pc, pp = i - cp * p.Pc;
+    org[i] = cp * p.H * p.Wd + (pp / p.Wout) * p.Wd + (pp % p.Wout);
   }
   __syncthreads();
 
@@ -96,23 +102,24 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastPar
   const long long hi = p.n_items * (blockIdx.x + 1) / gridDim.x;
   const int nblk = (p.Pc + 8 * kOctBlock - 1) / (8 * kOctBlock);
 
-  T a[4][KS];              // A fragments of the 4 row tiles (scaled inducing patches)
-  T em[4];                 // e_ref of row (8t + lr)
-  T acc[4];                // fwd: sigma^2 * sum_p w_p k   (partial over this lane's columns)
-  T dz[BWD ? 4 : 1][BWD ? DT : 1][2];
-  T s0[4], s2[4], Gm[4];
+  T a[NT][KS];              // A fragments of the 4 row tiles (scaled inducing patches)
+  T em[NT];                 // e_ref of row (8t + lr)
+  T acc[NT];                // fwd: sigma^2 * sum_p w_p k   (partial over this lane's columns)
+  T dz[BWD ? NT : 1][BWD ? DT : 1][2];
+  T s0[NT], s2[NT], Gm[NT];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) acc[t] = s0[t] = s2[t] = Gm[t] = em[t] = T(0);
+  for (int t = 0; t < NT; ++t) acc[t] = s0[t] = s2[t] = Gm[t] = em[t] = T(0);
   int cur_zkey = -1, cur_img = -1, cur_okey = -1;
   int zc = 0, zchunk = 0, on = 0, oc = 0, ochunk = 0;
   T sig2 = T(0), inv_l2 = T(0), lsg = T(1);
 
-  auto row_m = [&](int chunk, int t) { return chunk * (int)blockDim.x + warp * 32 + 8 * t + lr; };
+  const int rows_per_cta = (int)(blockDim.x >> 5) * 8 * NT;
+  auto row_m = [&](int chunk, int t) { return chunk * rows_per_cta + warp * 8 * NT + 8 * t + lr; };
 
   auto flush_out = [&]() {
     if constexpr (!BWD) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < NT; ++t) {
         const T v = quad_sum(acc[t]);
         const int m = row_m(ochunk, t);
         if (lc == 0 && m < p.M) {
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastPar
     if constexpr (BWD) {
       T t0 = T(0), t2 = T(0);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < NT; ++t) {
         const T s0m = quad_sum(s0[t]);  // total over the row's patches, in all 4 lanes of the quad
         t0 += s0[t];
         t2 += s2[t];
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastPar
       ochunk = chunk;
       if constexpr (BWD) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < NT; ++t) {
           const int m = row_m(chunk, t);
           size_t o = p.out_per_channel ? ((size_t)m * p.N + n) * p.C + c : (size_t)m * p.N + n;
           Gm[t] = m < p.M ? p.G[o] / p.Pn : T(0);
@@ -193,7 +200,7 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastPar
       lsg = p.ls[g];
       inv_l2 = T(1) / (lsg * lsg);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < NT; ++t) {
         const int m = row_m(chunk, t);
         const bool act = m < p.M;
         const T* zrow = p.Z + (size_t)(act ? m : 0) * p.Dtot + c * p.zplane;
@@ -218,23 +225,22 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastPar
       cur_img = n;
     }
 
-    const T* plane = img + c * p.H * p.Wd;
+    const int* orgc = org + c * p.Pc;
     const T* ep = e + c * p.Pc;
     const int woff = p.w_per_plane ? c * p.Pc : 0;
     const T* wp = w + woff;
-#pragma unroll 1
+#pragma unroll
     for (int ob = 0; ob < kOctBlock; ++ob) {
       const int p0 = (blk * kOctBlock + ob) * 8;
-      if (p0 >= p.Pc) break;
+      if (p0 >= p.Pc) continue;
       // ---- GEMM1: S[row][patch] = ref . patch
-      const int pB = min(p0 + lr, p.Pc - 1);
-      const T* bB = plane + (pB / p.Wout) * p.Wd + (pB % p.Wout);
+      const T* bB = img + orgc[min(p0 + lr, p.Pc - 1)];
       const int pC0 = p0 + 2 * lc;
       const bool v0 = pC0 < p.Pc, v1 = pC0 + 1 < p.Pc;
       const T e0 = ep[min(pC0, p.Pc - 1)], e1 = ep[min(pC0 + 1, p.Pc - 1)];
-      T cfr[4][2];
+      T cfr[NT][2];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < NT; ++t) {
         cfr[t][0] = em[t] + e0;
         cfr[t][1] = em[t] + e1;
       }
@@ -242,12 +248,12 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastPar
       for (int s = 0; s < KS; ++s) {
         const T b = bB[off1[s]];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) dmma(cfr[t], a[t][s], b);
+        for (int t = 0; t < NT; ++t) dmma(cfr[t], a[t][s], b);
       }
       const T w0 = v0 ? wp[pC0] : T(0), w1 = v1 ? wp[pC0 + 1] : T(0);
       if constexpr (!BWD) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < NT; ++t) {
           const T k0 = Math<T>::exp_arg(v0 ? cfr[t][0] : T(0), tbl);
           const T k1 = Math<T>::exp_arg(v1 ? cfr[t][1] : T(0), tbl);
           acc[t] = fma(w0 * sig2, k0, acc[t]);
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastPar
       } else {
         T vs0 = T(0), vs1 = T(0);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < NT; ++t) {
           const T a0 = v0 ? cfr[t][0] : T(0), a1 = v1 ? cfr[t][1] : T(0);
           const T g0 = Gm[t] * Math<T>::exp_arg(a0, tbl);
           const T g1 = Gm[t] * Math<T>::exp_arg(a1, tbl);
@@ -279,14 +285,13 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_mma_kernel(const FastPar
         // ---- GEMM2: dz[row][d] += coef[row][patch] * X[patch][d]
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int pK = min(p0 + 4 * h + lc, p.Pc - 1);
-          const T* bK = plane + (pK / p.Wout) * p.Wd + (pK % p.Wout);
+          const T* bK = img + orgc[min(p0 + 4 * h + lc, p.Pc - 1)];
           T b2[DT];
 #pragma unroll
           for (int dt = 0; dt < DT; ++dt) b2[dt] = bK[off2[dt]];
           const int src = (lane & ~3) | (2 * h + (lc >> 1));
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
+          for (int t = 0; t < NT; ++t) {
             const T x0 = __shfl_sync(0xffffffffu, cfr[t][0], src);
             const T x1 = __shfl_sync(0xffffffffu, cfr[t][1], src);
             const T a2 = (lc & 1) ? x1 : x0;
@@ -327,6 +332,7 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
   T* w = e + p.C * p.Pc;
   T* dWacc = w + nW;
   T* red = dWacc + (BWD ? nW : 0);
+  int* org = reinterpret_cast<int*>(red + 32);  // org[c*Pc + p]: offset of patch p's origin in the staged image
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
@@ -335,6 +341,10 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
   for (int i = tid; i < nW; i += blockDim.x) {
     w[i] = p.Wt ? p.Wt[i] : T(1);
     if (BWD) dWacc[i] = T(0);
+  }
+  for (int i = tid; i < p.C * p.Pc; i += blockDim.x) {
+    const int cp = i / p.Pc, pp = i - cp * p.Pc;
+    org[i] = cp * p.H * p.Wd + (pp / p.Wout) * p.Wd + (pp % p.Wout);
   }
   __syncthreads();
 
@@ -352,10 +362,7 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
   const T P2 = p.Pn * p.Pn;
 
   // patch index inside the domain -> offset of its origin in the staged image (planes stacked)
-  auto origin = [&](int cb, int pd) {
-    const int cp = pd / p.Pc, pp = pd - cp * p.Pc;
-    return (cb + cp) * p.H * p.Wd + (pp / p.Wout) * p.Wd + (pp % p.Wout);
-  };
+  auto origin = [&](int cb, int pd) { return org[cb * p.Pc + pd]; };
 
   T a[4][KS], em[4], wown[4];
   int own[4];
@@ -447,10 +454,10 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
       const size_t o = p.out_per_channel ? (size_t)n * p.C + dm : (size_t)n;
       gs = T(2) * sig2 * p.G[o] / P2;
     }
-#pragma unroll 1
+#pragma unroll
     for (int ob = 0; ob < kOctBlock; ++ob) {
       const int v0i = (blk * kOctBlock + ob) * 8;  // visit index of the octet's first column
-      if (v0i >= Lsweep) break;
+      if (v0i >= Lsweep) continue;
       // columns: B fragment lane lr, C fragment lanes 2*lc + {0,1}
       const int viB = min(v0i + lr, Lsweep - 1);
       int pB = wbase + viB;

@@ -49,8 +49,32 @@ def rectangles_rows(n):
     return np.array(rows)
 
 
+def save_case(case, path):
+    ok = case.oracle_kernel()
+    ref = case.twin_grads()
+    kuf, kd, kuu = ok.Kzx(case.Z, case.X), ok.Kdiag(case.X), ok.Kzz(case.Z)
+    assert np.max(np.abs(ref["kuf"] - kuf)) < 1e-13 * max(1.0, np.max(np.abs(kuf)))
+    np.savez_compressed(
+        path, X=case.X, Z=case.Z, W=np.ones(case.wshape()) if case.Wv is None else case.Wv, G=case.G, gd=case.gd,
+        Gu=case.Gu, kuf=kuf, kdiag=kd, kuu=kuu, dZ=ref["dZ"], dW=np.zeros(0) if ref["dW"] is None else ref["dW"],
+        dvar=np.concatenate([np.ravel(v) for v in ref["dvar"]]),
+        dls=np.concatenate([np.ravel(v) for v in ref["dls"]]))
+    return kuf
+
+
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
+    # reference outputs of every parametrised parity case: the GPU tests then do not depend on the
+    # CPU maths libraries of the GPU box (observed to drift by ~1e-9 on some hosts)
+    from tests.test_gpu_parity import CASES as PARITY_CASES, full_size_case
+    os.makedirs(os.path.join(out_dir, "parity"), exist_ok=True)
+    for case in PARITY_CASES:
+        save_case(case, os.path.join(out_dir, "parity", case.name + ".npz"))
+        print("parity", case.name)
+    big = full_size_case()
+    okb = big.oracle_kernel()
+    np.savez_compressed(os.path.join(out_dir, "parity", "cfg3_full_subsample.npz"),
+                        kuf=okb.Kzx(big.Z, big.X)[::15, ::10], kdiag=okb.Kdiag(big.X)[::10], kuu=okb.Kzz(big.Z)[::15, ::15])
     cases = golden_cases()
     if os.path.exists("/root/reference/datasets/rectangles.zip"):
         c = cases[0]
@@ -59,16 +83,7 @@ def main():
         pat = c.oracle_kernel(np.ones(c.wshape()))._get_patches(c.X).reshape(-1, c.geom.D)
         c.Z = pat[rng.permutation(len(pat))[:c.M]] + 0.001 * rng.rand(c.M, c.geom.D)
     for case in cases:
-        ok = case.oracle_kernel()
-        ref = case.twin_grads()
-        kuf, kd, kuu = ok.Kzx(case.Z, case.X), ok.Kdiag(case.X), ok.Kzz(case.Z)
-        assert np.max(np.abs(ref["kuf"] - kuf)) < 1e-13 * max(1.0, np.max(np.abs(kuf)))
-        np.savez_compressed(
-            os.path.join(out_dir, case.name + ".npz"), X=case.X, Z=case.Z,
-            W=np.ones(case.wshape()) if case.Wv is None else case.Wv, G=case.G, gd=case.gd, Gu=case.Gu,
-            kuf=kuf, kdiag=kd, kuu=kuu, dZ=ref["dZ"], dW=np.zeros(0) if ref["dW"] is None else ref["dW"],
-            dvar=np.concatenate([np.ravel(v) for v in ref["dvar"]]),
-            dls=np.concatenate([np.ravel(v) for v in ref["dls"]]))
+        kuf = save_case(case, os.path.join(out_dir, case.name + ".npz"))
         print(case.name, kuf.shape, float(np.abs(kuf).max()))
 
 
