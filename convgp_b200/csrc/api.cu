@@ -262,7 +262,7 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     size_t bytes = sizeof(T) * (size_t)M * N * (p.out_per_channel ? d->C : 1);
     CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
   }
-  static const int use_mma = env_choice(BWD ? "CGP_KUF_BWD" : "CGP_KUF_FWD", BWD ? 0 : 1);
+  static const int use_mma = env_choice(BWD ? "CGP_KUF_BWD" : "CGP_KUF_FWD", 1);
   if constexpr (std::is_same<T, double>::value) if (use_mma) {
     // float64: FP64 MMA kernels, work items are blocks of kOctBlock patch octets
     static const int nt = env_choice("CGP_KUF_TILES", 4);  // row tiles per warp (2 or 4)
@@ -302,9 +302,11 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
   // C*P' patches of the image pair with each other (Conv with colour_channels > 1)
   p.ndom = (mode == 2 || p.out_per_channel) ? d->C : 1;
   const int ppd = d->C / p.ndom, Pd = ppd * g.Pc, Hd = ppd * g.Hout;
-  static const int use_mma = env_choice(BWD ? "CGP_KDIAG_BWD" : "CGP_KDIAG_FWD", 0);
-  static const int max_warps = env_choice("CGP_KDIAG_WARPS", 8);
+  static const int use_mma = env_choice(BWD ? "CGP_KDIAG_BWD" : "CGP_KDIAG_FWD", 1);
   const bool mma_path = std::is_same<T, double>::value && use_mma;
+  // the MMA kernels hold ~200-250 registers per thread: small CTAs keep several resident per SM
+  static const int max_warps_env = env_choice("CGP_KDIAG_WARPS", 0);
+  const int max_warps = max_warps_env > 0 ? max_warps_env : (mma_path ? 2 : 8);
   const int tpb = 32 * pick_warps(Pd, std::min(3, max_warps), max_warps);
   const int nchunk = (Pd + tpb - 1) / tpb;
   if (!BWD) {

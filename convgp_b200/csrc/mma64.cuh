@@ -46,8 +46,13 @@ constexpr int kOctBlock = 3;  // octets per work item
 template <int PH, int PW>
 struct MmaGeom {
   static constexpr int D = PH * PW;
-  static constexpr int KS = (D + 3) / 4;  // GEMM1 k-steps
-  static constexpr int DT = (D + 7) / 8;  // GEMM2 column tiles
+  // GEMM1 (K = patch dims, steps of 4): a remainder of 1-2 dims is cheaper as scalar FMAs on the
+  // C fragments than as a mostly-empty MMA step (D = 25 -> 6 steps + 1 dim, D = 9 -> 2 + 1).
+  static constexpr int R1 = (D % 4 != 0 && D % 4 <= 2 && D >= 4) ? D % 4 : 0;
+  static constexpr int KS = R1 ? D / 4 : (D + 3) / 4;
+  // GEMM2 (N = patch dims, tiles of 8): same for its column tiles (D = 25 -> 3 tiles + 1 dim).
+  static constexpr int R2 = (D % 8 != 0 && D % 8 <= 2 && D >= 8) ? D % 8 : 0;
+  static constexpr int DT = R2 ? D / 8 : (D + 7) / 8;
 };
 
 // offset of patch element d inside the plane, relative to the patch origin (0 for padding dims)
@@ -64,7 +69,7 @@ template <int PH, int PW, bool BWD, int NT>
 __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 4)) kuf_mma_kernel(const FastParams<double> p) {
   using T = double;
   using MG = MmaGeom<PH, PW>;
-  constexpr int D = MG::D, KS = MG::KS, DT = MG::DT;
+  constexpr int D = MG::D, KS = MG::KS, DT = MG::DT, R1 = MG::R1, R2 = MG::R2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tbl = reinterpret_cast<T*>(smem_raw);
   T* img = tbl + Math<T>::kTableDoubles;
@@ -102,7 +107,14 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
   const long long hi = p.n_items * (blockIdx.x + 1) / gridDim.x;
   const int nblk = (p.Pc + 8 * kOctBlock - 1) / (8 * kOctBlock);
 
-  T a[NT][KS];              // A fragments of the 4 row tiles (scaled inducing patches)
+  T a[NT][KS];              // A fragments of the row tiles (scaled inducing patches)
+  T ar[NT][R1 ? R1 : 1];    // remainder dims of row (8t + lr), C-fragment row layout
+  T dzr[BWD ? NT : 1][R2 ? R2 : 1];  // bwd: remainder columns of dz, partial over this lane's patches
+  int offr1[R1 ? R1 : 1], offr2[R2 ? R2 : 1];
+#pragma unroll
+  for (int r = 0; r < R1; ++r) offr1[r] = elem_off<PH, PW>(4 * KS + r, p.Wd);
+#pragma unroll
+  for (int r = 0; r < R2; ++r) offr2[r] = elem_off<PH, PW>(8 * DT + r, p.Wd);
   T em[NT];                 // e_ref of row (8t + lr)
   T acc[NT];                // fwd: sigma^2 * sum_p w_p k   (partial over this lane's columns)
   T dz[BWD ? NT : 1][BWD ? DT : 1][2];
@@ -149,6 +161,17 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
               const int d = 8 * dt + 2 * lc + x;
               if (d < D) atomicAdd(drow + d * p.zstride, sig2 * inv_l2 * (dz[t][dt][x] - zrow[d * p.zstride] * s0m));
             }
+        }
+#pragma unroll
+        for (int r = 0; r < R2; ++r) {
+          const T tot = quad_sum(dzr[t][r]);
+          const int d = 8 * DT + r;
+          if (lc == 0 && m < p.M && p.dZ) {
+            const T* zrow = p.Z + (size_t)m * p.Dtot + zc * p.zplane;
+            atomicAdd(p.dZ + (size_t)m * p.Dtot + zc * p.zplane + d * p.zstride,
+                      sig2 * inv_l2 * (tot - zrow[d * p.zstride] * s0m));
+          }
+          dzr[t][r] = T(0);
         }
         s0[t] = s2[t] = T(0);
 #pragma unroll
@@ -212,10 +235,18 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
           a[t][s] = zv * inv_l2;
           zz = fma(zv, zv, zz);
         }
+#pragma unroll
+        for (int r = 0; r < R1; ++r) {
+          const T zv = act ? zrow[(4 * KS + r) * p.zstride] : T(0);
+          ar[t][r] = zv * inv_l2;
+          if (lc == 0) zz = fma(zv, zv, zz);  // every lane of the quad holds it; count it once
+        }
         em[t] = T(-0.5) * inv_l2 * quad_sum(zz);
         if constexpr (BWD) {
 #pragma unroll
           for (int dt = 0; dt < DT; ++dt) dz[t][dt][0] = dz[t][dt][1] = T(0);
+#pragma unroll
+          for (int r = 0; r < R2; ++r) dzr[t][r] = T(0);
         }
       }
     }
@@ -250,6 +281,17 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
 #pragma unroll
         for (int t = 0; t < NT; ++t) dmma(cfr[t], a[t][s], b);
       }
+      const T* xc0 = img + orgc[min(pC0, p.Pc - 1)];      // this lane's two C-fragment columns (patches)
+      const T* xc1 = img + orgc[min(pC0 + 1, p.Pc - 1)];
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        const T x0 = xc0[offr1[r]], x1 = xc1[offr1[r]];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          cfr[t][0] = fma(ar[t][r], x0, cfr[t][0]);
+          cfr[t][1] = fma(ar[t][r], x1, cfr[t][1]);
+        }
+      }
       const T w0 = v0 ? wp[pC0] : T(0), w1 = v1 ? wp[pC0 + 1] : T(0);
       if constexpr (!BWD) {
 #pragma unroll
@@ -280,6 +322,15 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
           if (lr == 0) {
             if (v0) atomicAdd(dWacc + woff + pC0, vs0 * sig2);
             if (v1) atomicAdd(dWacc + woff + pC0 + 1, vs1 * sig2);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R2; ++r) {
+          const T x0 = xc0[offr2[r]], x1 = xc1[offr2[r]];
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            dzr[t][r] = fma(cfr[t][0], x0, dzr[t][r]);
+            dzr[t][r] = fma(cfr[t][1], x1, dzr[t][r]);
           }
         }
         // ---- GEMM2: dz[row][d] += coef[row][patch] * X[patch][d]
@@ -323,7 +374,7 @@ template <int PH, int PW, bool BWD>
 __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<double> p) {
   using T = double;
   using MG = MmaGeom<PH, PW>;
-  constexpr int D = MG::D, KS = MG::KS;
+  constexpr int D = MG::D, KS = MG::KS, R1 = MG::R1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tbl = reinterpret_cast<T*>(smem_raw);
   T* img = tbl + Math<T>::kTableDoubles;
@@ -365,6 +416,10 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
   auto origin = [&](int cb, int pd) { return org[cb * p.Pc + pd]; };
 
   T a[4][KS], em[4], wown[4];
+  T ar[4][R1 ? R1 : 1];
+  int offr1[R1 ? R1 : 1];
+#pragma unroll
+  for (int r = 0; r < R1; ++r) offr1[r] = elem_off<PH, PW>(4 * KS + r, p.Wd);
   int own[4];
   T acc[4], acc2[4], dwown[4];
 #pragma unroll
@@ -441,6 +496,8 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
         const T* base = img + origin(cb, act ? own[t] : 0);
 #pragma unroll
         for (int s = 0; s < KS; ++s) a[t][s] = (act && 4 * s + lc < D) ? base[off1[s]] * sc : T(0);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) ar[t][r] = act ? base[offr1[r]] * sc : T(0);
         em[t] = act ? e[cb * p.Pc + own[t]] : T(0);
         wown[t] = act ? w[(p.w_per_plane ? cb * p.Pc : 0) + own[t]] : T(0);
       }
@@ -480,6 +537,15 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
         const T b = bB[off1[s]];
 #pragma unroll
         for (int t = 0; t < 4; ++t) dmma(cfr[t], a[t][s], b);
+      }
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        const T x0 = img[origin(cb, q0) + offr1[r]], x1 = img[origin(cb, q1) + offr1[r]];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          cfr[t][0] = fma(ar[t][r], x0, cfr[t][0]);
+          cfr[t][1] = fma(ar[t][r], x1, cfr[t][1]);
+        }
       }
       const T w0 = c0 ? wp[q0] : T(0), w1 = c1 ? wp[q1] : T(0);
       T sc0 = T(0), sc1 = T(0);
