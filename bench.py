@@ -224,7 +224,7 @@ def run_gpu(args):
     import ctypes
     peaks = {}
     if rank == 0:
-        for kind, name in ((0, "fp64_fma"), (1, "fp32_fma"), (2, "mufu_ex2"), (3, "f64_exp")):
+        for kind, name in ((0, "fp64_fma"), (1, "fp32_fma"), (2, "mufu_ex2"), (3, "f64_exp"), (4, "fp64_mma")):
             v = ctypes.c_double()
             _lib.check(_lib.lib().cgp_peak_probe(kind, ctypes.byref(v)))
             peaks[name] = v.value
@@ -353,9 +353,12 @@ def run_gpu(args):
     # ---- roofline
     work = algorithmic_work(N_BATCH)
     if args.dtype == "f64":
+        fma_rate = max(peaks["fp64_fma"], peaks["fp64_mma"])  # DMMA and DFMA share the pipe; DMMA is the faster feed
+
         def t_bound(fl, ex):
-            return fl / (2 * peaks["fp64_fma"]) + ex / peaks["f64_exp"]
-        pipe, peak_note = "fp64", "FP64 pipe: flops/(2*DFMA rate) + exps/(library exp rate), both probed on this GPU"
+            return fl / (2 * fma_rate) + ex / peaks["f64_exp"]
+        pipe, peak_note = "fp64", ("FP64 pipe: flops/(2*max(DFMA, DMMA) rate) + exps/(library exp rate), all probed on "
+                                   "this GPU by cgp_peak_probe (MEASURED_PEAKS.json has no FP64 figure)")
     else:
         def t_bound(fl, ex):
             return max(fl / (2 * peaks["fp32_fma"]), ex / peaks["mufu_ex2"])
@@ -371,6 +374,11 @@ def run_gpu(args):
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.dtype, {}).get(dom)
     except Exception:
         pass
     images = N_BATCH * world
@@ -390,7 +398,7 @@ def run_gpu(args):
                    "collective": "NCCL all-reduce of the packed gradient buffer per step" if world > 1 else "none"},
         "roofline": {
             "bound": pipe, "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_note,
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_note,
             "kernel_ms": per_kernel, "step_frac": step_frac,
             "probes": peaks,
             "hbm": {"algorithmic_bytes_per_step": algorithmic_bytes(N_BATCH, es),
