@@ -202,6 +202,8 @@ def run_gpu(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     dt = torch.float64 if args.dtype == "f64" else torch.float32
     es = 8 if args.dtype == "f64" else 4
