@@ -75,6 +75,12 @@ def main():
     okb = big.oracle_kernel()
     np.savez_compressed(os.path.join(out_dir, "parity", "cfg3_full_subsample.npz"),
                         kuf=okb.Kzx(big.Z, big.X)[::15, ::10], kdiag=okb.Kdiag(big.X)[::10], kuu=okb.Kzz(big.Z)[::15, ::15])
+    from tests.test_gpu_parity import full_size_cifar_cases
+    for c in full_size_cifar_cases():
+        okc = c.oracle_kernel()
+        np.savez_compressed(os.path.join(out_dir, "parity", c.name + "_subsample.npz"),
+                            kuf=okc.Kzx(c.Z, c.X)[::25, ::2], kdiag=okc.Kdiag(c.X))
+        print("parity", c.name)
     cases = golden_cases()
     if os.path.exists("/root/reference/datasets/rectangles.zip"):
         c = cases[0]

@@ -120,3 +120,31 @@ def test_full_size_mnist_kuf_kdiag_f64():
     k.W = 2.0 * case.Wv
     assert rel_err(k.Kzx(Z, X).detach().cpu().numpy(), 2.0 * kuf) < 1e-13
     assert rel_err(k.Kdiag(X).detach().cpu().numpy(), 4.0 * kd) < 1e-13
+
+
+def full_size_cifar_cases():
+    """BASELINE config 5 (cifar.py -k addwconv: 32x32x3, 5x5x3 colour patches, one RBF per channel, M=1000,
+    N=30) and the per-channel kernels of cifar.py -k wconv / multi at full geometry (M reduced to 250)."""
+    S = np.s_
+    return [
+        Case("cfg5_full", "colour", 32, 32, 3, 5, 5,
+             [(1.004, 0.5, S[0::3], False), (0.991, 0.5, S[1::3], False), (1.013, 0.5, S[2::3], False)],
+             N=30, M=1000, seed=21, xdist="uint8"),
+        Case("cifar_wconv_full", "conv", 32, 32, 3, 5, 5, [(1.0, 1.0, None, False)], N=8, M=250, seed=22, xdist="uint8"),
+        Case("cifar_multi_full", "multi", 32, 32, 3, 5, 5, [(1.0, 1.0, None, False)], N=8, M=250, seed=23, xdist="uint8"),
+    ]
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2], ids=["cfg5_full", "cifar_wconv_full", "cifar_multi_full"])
+def test_full_size_cifar_shapes_f64(idx):
+    import os
+    case = full_size_cifar_cases()[idx]
+    from convgp_b200.kernels import as_tensor
+    k = case.package_kernel()
+    X, Z = as_tensor(case.X), as_tensor(case.Z)
+    kuf = k.Kzx(Z, X).detach().cpu().numpy()
+    kd = k.Kdiag(X).detach().cpu().numpy()
+    sub = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "parity",
+                               case.name + "_subsample.npz"))
+    assert rel_err(kuf[::25, ::2], sub["kuf"]) < 1e-10
+    assert rel_err(kd, sub["kdiag"]) < 1e-10
