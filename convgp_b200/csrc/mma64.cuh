@@ -17,6 +17,8 @@
 // shared-memory image -- patches are never materialised.  Fragment layouts (PTX ISA, m8n8k4 .f64):
 //   A[row = lane>>2][k = lane&3]   B[k = lane&3][col = lane>>2]   C[row = lane>>2][col = 2*(lane&3) + {0,1}]
 #pragma once
+#include <type_traits>
+
 #include "fast.cuh"
 
 namespace cgp {
@@ -260,16 +262,17 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
     const T* ep = e + c * p.Pc;
     const int woff = p.w_per_plane ? c * p.Pc : 0;
     const T* wp = w + woff;
-#pragma unroll
-    for (int ob = 0; ob < kOctBlock; ++ob) {
-      const int p0 = (blk * kOctBlock + ob) * 8;
-      if (p0 >= p.Pc) continue;
-      // ---- GEMM1: S[row][patch] = ref . patch
-      const T* bB = img + orgc[min(p0 + lr, p.Pc - 1)];
+    // One octet = two stages.  gemm1: C fragments <- e_ref + e_patch + ref . patch (DMMA + remainder
+    // dims).  epilogue: exp, weights, (bwd) coefficient shuffles + GEMM2.  FULL octets (all 8 patches
+    // valid) carry no masks.  For a full item the three octets are issued software-pipelined in one
+    // basic block -- gemm1 of the next octet ahead of the epilogue of the current one -- so the DMMA
+    // stream of one octet fills the dependency bubbles of the previous octet's exp chains.
+    auto gemm1 = [&](int p0, auto full_c, T (&cfr)[NT][2]) {
+      constexpr bool FULL = decltype(full_c)::value;
+      const T* bB = img + orgc[FULL ? p0 + lr : min(p0 + lr, p.Pc - 1)];
       const int pC0 = p0 + 2 * lc;
-      const bool v0 = pC0 < p.Pc, v1 = pC0 + 1 < p.Pc;
-      const T e0 = ep[min(pC0, p.Pc - 1)], e1 = ep[min(pC0 + 1, p.Pc - 1)];
-      T cfr[NT][2];
+      const int i0 = FULL ? pC0 : min(pC0, p.Pc - 1), i1 = FULL ? pC0 + 1 : min(pC0 + 1, p.Pc - 1);
+      const T e0 = ep[i0], e1 = ep[i1];
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         cfr[t][0] = em[t] + e0;
@@ -281,8 +284,8 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
 #pragma unroll
         for (int t = 0; t < NT; ++t) dmma(cfr[t], a[t][s], b);
       }
-      const T* xc0 = img + orgc[min(pC0, p.Pc - 1)];      // this lane's two C-fragment columns (patches)
-      const T* xc1 = img + orgc[min(pC0 + 1, p.Pc - 1)];
+      const T* xc0 = img + orgc[i0];  // this lane's two C-fragment columns (patches)
+      const T* xc1 = img + orgc[i1];
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
         const T x0 = xc0[offr1[r]], x1 = xc1[offr1[r]];
@@ -292,14 +295,21 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
           cfr[t][1] = fma(ar[t][r], x1, cfr[t][1]);
         }
       }
-      const T w0 = v0 ? wp[pC0] : T(0), w1 = v1 ? wp[pC0 + 1] : T(0);
+    };
+    auto epilogue = [&](int p0, auto full_c, T (&cfr)[NT][2]) {
+      constexpr bool FULL = decltype(full_c)::value;
+      const int pC0 = p0 + 2 * lc;
+      const bool v0 = FULL || pC0 < p.Pc, v1 = FULL || pC0 + 1 < p.Pc;
+      const int i0 = FULL ? pC0 : min(pC0, p.Pc - 1), i1 = FULL ? pC0 + 1 : min(pC0 + 1, p.Pc - 1);
+      const T w0 = v0 ? wp[i0] : T(0), w1 = v1 ? wp[i1] : T(0);
       if constexpr (!BWD) {
+        const T ws0 = w0 * sig2, ws1 = w1 * sig2;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           const T k0 = Math<T>::exp_arg(v0 ? cfr[t][0] : T(0), tbl);
           const T k1 = Math<T>::exp_arg(v1 ? cfr[t][1] : T(0), tbl);
-          acc[t] = fma(w0 * sig2, k0, acc[t]);
-          acc[t] = fma(w1 * sig2, k1, acc[t]);
+          acc[t] = fma(ws0, k0, acc[t]);
+          acc[t] = fma(ws1, k1, acc[t]);
         }
       } else {
         T vs0 = T(0), vs1 = T(0);
@@ -324,6 +334,8 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
             if (v1) atomicAdd(dWacc + woff + pC0 + 1, vs1 * sig2);
           }
         }
+        const T* xc0 = img + orgc[i0];
+        const T* xc1 = img + orgc[i1];
 #pragma unroll
         for (int r = 0; r < R2; ++r) {
           const T x0 = xc0[offr2[r]], x1 = xc1[offr2[r]];
@@ -336,7 +348,8 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
         // ---- GEMM2: dz[row][d] += coef[row][patch] * X[patch][d]
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const T* bK = img + orgc[min(p0 + 4 * h + lc, p.Pc - 1)];
+          const int pk = p0 + 4 * h + lc;
+          const T* bK = img + orgc[FULL ? pk : min(pk, p.Pc - 1)];
           T b2[DT];
 #pragma unroll
           for (int dt = 0; dt < DT; ++dt) b2[dt] = bK[off2[dt]];
@@ -350,6 +363,35 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
             for (int dt = 0; dt < DT; ++dt) dmma(dz[t][dt], a2, b2[dt]);
           }
         }
+      }
+    };
+    const int pfirst = blk * kOctBlock * 8;
+    if (pfirst + 8 * kOctBlock <= p.Pc) {
+      static_assert(kOctBlock == 3, "the pipelined issue order below is written for 3 octets");
+      T c0[NT][2];
+      if constexpr (!BWD) {
+        T c1[NT][2];
+        gemm1(pfirst, std::true_type{}, c0);
+        gemm1(pfirst + 8, std::true_type{}, c1);
+        epilogue(pfirst, std::true_type{}, c0);
+        gemm1(pfirst + 16, std::true_type{}, c0);
+        epilogue(pfirst + 8, std::true_type{}, c1);
+        epilogue(pfirst + 16, std::true_type{}, c0);
+      } else {  // the backward pass is at the register limit: one octet in flight
+#pragma unroll
+        for (int ob = 0; ob < kOctBlock; ++ob) {
+          gemm1(pfirst + 8 * ob, std::true_type{}, c0);
+          epilogue(pfirst + 8 * ob, std::true_type{}, c0);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int ob = 0; ob < kOctBlock; ++ob) {
+        const int p0 = pfirst + 8 * ob;
+        if (p0 >= p.Pc) break;
+        T c0[NT][2];
+        gemm1(p0, std::false_type{}, c0);
+        epilogue(p0, std::false_type{}, c0);
       }
     }
   }
@@ -511,18 +553,17 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
       const size_t o = p.out_per_channel ? (size_t)n * p.C + dm : (size_t)n;
       gs = T(2) * sig2 * p.G[o] / P2;
     }
-#pragma unroll
-    for (int ob = 0; ob < kOctBlock; ++ob) {
-      const int v0i = (blk * kOctBlock + ob) * 8;  // visit index of the octet's first column
-      if (v0i >= Lsweep) continue;
+    // INTERIOR octets: every (own row, column) pair of the tile has 0 < delta < P/2, i.e. weight 2
+    // and no masks -- all but the first four and last four octets of a warp's sweep.
+    auto octet = [&](int v0i, auto interior_c) {
+      constexpr bool INT = decltype(interior_c)::value;
       // columns: B fragment lane lr, C fragment lanes 2*lc + {0,1}
-      const int viB = min(v0i + lr, Lsweep - 1);
-      int pB = wbase + viB;
+      int pB = wbase + (INT ? v0i + lr : min(v0i + lr, Lsweep - 1));
       pB -= pB >= Pd ? Pd : 0;
       const T* bB = img + origin(cb, pB);
       const int vi0 = v0i + 2 * lc, vi1 = vi0 + 1;
-      const bool c0 = vi0 < Lsweep, c1 = vi1 < Lsweep;
-      int q0 = wbase + min(vi0, Lsweep - 1), q1 = wbase + min(vi1, Lsweep - 1);
+      const bool c0 = INT || vi0 < Lsweep, c1 = INT || vi1 < Lsweep;
+      int q0 = wbase + (INT ? vi0 : min(vi0, Lsweep - 1)), q1 = wbase + (INT ? vi1 : min(vi1, Lsweep - 1));
       q0 -= q0 >= Pd ? Pd : 0;
       q1 -= q1 >= Pd ? Pd : 0;
       const T e0 = ep[q0], e1 = ep[q1];
@@ -551,25 +592,39 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
       T sc0 = T(0), sc1 = T(0);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        // pair weights from the cyclic distance (own -> column)
-        int d0 = q0 - own[t], d1 = q1 - own[t];
-        d0 += d0 < 0 ? Pd : 0;
-        d1 += d1 < 0 ? Pd : 0;
-        int wt0 = d0 == 0 ? 1 : (d0 < half || (!even && d0 == half)) ? 2 : (even && d0 == half) ? 1 : 0;
-        int wt1 = d1 == 0 ? 1 : (d1 < half || (!even && d1 == half)) ? 2 : (even && d1 == half) ? 1 : 0;
-        if (!c0 || own[t] >= Pd) wt0 = 0;
-        if (!c1 || own[t] >= Pd) wt1 = 0;
-        const T a0 = wt0 ? cfr[t][0] : T(0), a1 = wt1 ? cfr[t][1] : T(0);
-        const T k0 = Math<T>::exp_arg(a0, tbl), k1 = Math<T>::exp_arg(a1, tbl);
-        const T wk0 = w0 * k0, wk1 = w1 * k1;
-        acc[t] = fma((T)wt0, wk0, acc[t]);
-        acc[t] = fma((T)wt1, wk1, acc[t]);
-        if constexpr (BWD) {
-          acc2[t] = fma((T)wt0 * wk0, a0, acc2[t]);
-          acc2[t] = fma((T)wt1 * wk1, a1, acc2[t]);
-          dwown[t] += (wt0 ? wk0 : T(0)) + (wt1 ? wk1 : T(0));
-          sc0 = fma(wt0 == 2 ? wown[t] : T(0), k0, sc0);
-          sc1 = fma(wt1 == 2 ? wown[t] : T(0), k1, sc1);
+        if constexpr (INT) {
+          const T a0 = cfr[t][0], a1 = cfr[t][1];
+          const T k0 = Math<T>::exp_arg(a0, tbl), k1 = Math<T>::exp_arg(a1, tbl);
+          const T wk0 = w0 * k0, wk1 = w1 * k1;
+          acc[t] += T(2) * (wk0 + wk1);
+          if constexpr (BWD) {
+            acc2[t] = fma(T(2) * wk0, a0, acc2[t]);
+            acc2[t] = fma(T(2) * wk1, a1, acc2[t]);
+            dwown[t] += wk0 + wk1;
+            sc0 = fma(wown[t], k0, sc0);
+            sc1 = fma(wown[t], k1, sc1);
+          }
+        } else {
+          // pair weights from the cyclic distance (own -> column)
+          int d0 = q0 - own[t], d1 = q1 - own[t];
+          d0 += d0 < 0 ? Pd : 0;
+          d1 += d1 < 0 ? Pd : 0;
+          int wt0 = d0 == 0 ? 1 : (d0 < half || (!even && d0 == half)) ? 2 : (even && d0 == half) ? 1 : 0;
+          int wt1 = d1 == 0 ? 1 : (d1 < half || (!even && d1 == half)) ? 2 : (even && d1 == half) ? 1 : 0;
+          if (!c0 || own[t] >= Pd) wt0 = 0;
+          if (!c1 || own[t] >= Pd) wt1 = 0;
+          const T a0 = wt0 ? cfr[t][0] : T(0), a1 = wt1 ? cfr[t][1] : T(0);
+          const T k0 = Math<T>::exp_arg(a0, tbl), k1 = Math<T>::exp_arg(a1, tbl);
+          const T wk0 = w0 * k0, wk1 = w1 * k1;
+          acc[t] = fma((T)wt0, wk0, acc[t]);
+          acc[t] = fma((T)wt1, wk1, acc[t]);
+          if constexpr (BWD) {
+            acc2[t] = fma((T)wt0 * wk0, a0, acc2[t]);
+            acc2[t] = fma((T)wt1 * wk1, a1, acc2[t]);
+            dwown[t] += (wt0 ? wk0 : T(0)) + (wt1 ? wk1 : T(0));
+            sc0 = fma(wt0 == 2 ? wown[t] : T(0), k0, sc0);
+            sc1 = fma(wt1 == 2 ? wown[t] : T(0), k1, sc1);
+          }
         }
       }
       if constexpr (BWD) {
@@ -582,6 +637,15 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
           }
         }
       }
+    };
+    const bool warp_full = wbase + 31 < Pd;
+#pragma unroll
+    for (int ob = 0; ob < kOctBlock; ++ob) {
+      const int v0i = (blk * kOctBlock + ob) * 8;  // visit index of the octet's first column
+      if (v0i >= Lsweep) continue;
+      // delta = vi - k, k in [0, 31]: interior iff 0 < v0i - 31 and v0i + 7 < half (and inside the sweep)
+      if (warp_full && v0i >= 32 && v0i + 7 < half && v0i + 7 < Lsweep) octet(v0i, std::true_type{});
+      else octet(v0i, std::false_type{});
     }
   }
   if (cur_key >= 0) flush();

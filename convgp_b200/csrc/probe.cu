@@ -15,7 +15,27 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, double* sink, dou
     Math<double>::init_table(tbl);
     __syncthreads();
   }
-  if (KIND == 11 || KIND == 12 || KIND == 13) {  // DMMA with 1 / 2 / 4 dependent chains, one warp per sub-partition
+  if (KIND == 14 || KIND == 15) {  // DMMA with a distinct A register per instruction (14) and distinct A and B (15)
+    double acc[kChains][2], a[kChains], b[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+      acc[i][0] = i;
+      acc[i][1] = -i;
+      a[i] = seed + i + tid * 1e-6;
+      b[i] = 1.0 + (seed + i) * 1e-9;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < kChains; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[i][0]), "+d"(acc[i][1])
+                     : "d"(a[i]), "d"(KIND == 15 ? b[i] : b[0]));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += acc[i][0] + acc[i][1] + a[i] + b[i];
+    if (s == 12345.678) sink[0] = s;
+  } else if (KIND == 11 || KIND == 12 || KIND == 13) {  // DMMA with 1 / 2 / 4 dependent chains, one warp per sub-partition
     constexpr int NC = KIND == 11 ? 1 : (KIND == 12 ? 2 : 4);
     double acc[NC][2], a = seed + tid * 1e-6, b = 1.0 + seed * 1e-9;
 #pragma unroll
@@ -212,6 +232,9 @@ extern "C" int cgp_peak_probe(int32_t kind, double* ops_per_s) {
     case 11: return run_probe<11>(64.0, ops_per_s);
     case 12: return run_probe<12>(64.0, ops_per_s);
     case 13: return run_probe<13>(64.0, ops_per_s);
+    // DMMA operand-fetch sensitivity: distinct A (14), distinct A and B (15) per instruction
+    case 14: return run_probe<14>(kChains * 8.0, ops_per_s);
+    case 15: return run_probe<15>(kChains * 8.0, ops_per_s);
     default:
       set_error("unknown probe kind %d", kind);
       return CGP_ERR_BAD_DESC;
