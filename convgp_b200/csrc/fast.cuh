@@ -210,14 +210,27 @@ __global__ void __launch_bounds__(128, BWD ? (sizeof(T) == 8 ? 2 : 3) : 4) kuf_f
     }
   };
 
-  for (long long it = lo; it < hi; ++it) {
-    long long t = it;
-    const int r = (int)(t % p.Hout);
+  int r, c, n, chunk;  // item = (chunk, n, c, r), r fastest: decode once, then count
+  {
+    long long t = lo;
+    r = (int)(t % p.Hout);
     t /= p.Hout;
-    const int c = (int)(t % p.C);
+    c = (int)(t % p.C);
     t /= p.C;
-    const int n = (int)(t % p.N);
-    const int chunk = (int)(t / p.N);
+    n = (int)(t % p.N);
+    chunk = (int)(t / p.N);
+  }
+  for (long long it = lo; it < hi; ++it, ++r) {
+    if (r == p.Hout) {
+      r = 0;
+      if (++c == p.C) {
+        c = 0;
+        if (++n == p.N) {
+          n = 0;
+          ++chunk;
+        }
+      }
+    }
     const int m = chunk * blockDim.x + tid;
     const bool active = m < p.M;
 
@@ -397,14 +410,27 @@ __global__ void __launch_bounds__(kMaxTPB) kdiag_fast_kernel(const FastParams<T>
     dwown = T(0);
   };
 
-  for (long long it = lo; it < hi; ++it) {
-    long long t = it;
-    const int s = (int)(t % p.S);
+  int s, j, dm, n;
+  {
+    long long t = lo;
+    s = (int)(t % p.S);
     t /= p.S;
-    const int j = (int)(t % nchunk);
+    j = (int)(t % nchunk);
     t /= nchunk;
-    const int dm = (int)(t % ndom);
-    const int n = (int)(t / ndom);
+    dm = (int)(t % ndom);
+    n = (int)(t / ndom);
+  }
+  for (long long it = lo; it < hi; ++it, ++s) {
+    if (s == p.S) {
+      s = 0;
+      if (++j == nchunk) {
+        j = 0;
+        if (++dm == ndom) {
+          dm = 0;
+          ++n;
+        }
+      }
+    }
     const int cb = (ndom == 1) ? 0 : dm;  // first plane of the domain
     const int key = (n * ndom + dm) * nchunk + j;
     if (key != cur_key) {

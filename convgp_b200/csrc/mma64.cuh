@@ -189,14 +189,29 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
     }
   };
 
-  for (long long it = lo; it < hi; ++it) {
-    long long tt = it;
-    const int blk = (int)(tt % nblk);
+  // item = (chunk, n, c, blk), blk fastest: decode once, then count (64-bit div/mod per item costs
+  // as many issue slots as an octet's worth of exps)
+  int blk, c, n, chunk;
+  {
+    long long tt = lo;
+    blk = (int)(tt % nblk);
     tt /= nblk;
-    const int c = (int)(tt % p.C);
+    c = (int)(tt % p.C);
     tt /= p.C;
-    const int n = (int)(tt % p.N);
-    const int chunk = (int)(tt / p.N);
+    n = (int)(tt % p.N);
+    chunk = (int)(tt / p.N);
+  }
+  for (long long it = lo; it < hi; ++it, ++blk) {
+    if (blk == nblk) {
+      blk = 0;
+      if (++c == p.C) {
+        c = 0;
+        if (++n == p.N) {
+          n = 0;
+          ++chunk;
+        }
+      }
+    }
 
     const int zkey = chunk * p.C + (p.zplane || p.grp_per_plane ? c : 0);
     const int okey = (chunk * p.N + n) * p.C + (p.out_per_channel ? c : 0);
@@ -506,14 +521,27 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
     for (int t = 0; t < 4; ++t) acc[t] = acc2[t] = dwown[t] = T(0);
   };
 
-  for (long long it = lo; it < hi; ++it) {
-    long long tt = it;
-    const int blk = (int)(tt % p.S);
+  int blk, j, dm, n;
+  {
+    long long tt = lo;
+    blk = (int)(tt % p.S);
     tt /= p.S;
-    const int j = (int)(tt % nchunk);
+    j = (int)(tt % nchunk);
     tt /= nchunk;
-    const int dm = (int)(tt % ndom);
-    const int n = (int)(tt / ndom);
+    dm = (int)(tt % ndom);
+    n = (int)(tt / ndom);
+  }
+  for (long long it = lo; it < hi; ++it, ++blk) {
+    if (blk == p.S) {
+      blk = 0;
+      if (++j == nchunk) {
+        j = 0;
+        if (++dm == ndom) {
+          dm = 0;
+          ++n;
+        }
+      }
+    }
     const int cb = (ndom == 1) ? 0 : dm;
     const int key = (n * ndom + dm) * nchunk + j;
     const int wbase = j * blockDim.x + warp * 32;  // first own patch of this warp
