@@ -15,7 +15,28 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, double* sink, dou
     Math<double>::init_table(tbl);
     __syncthreads();
   }
-  if (KIND == 14 || KIND == 15) {  // DMMA with a distinct A register per instruction (14) and distinct A and B (15)
+  if (KIND == 16) {  // legacy-path tensor MMA: mma.sync.m16n8k8 tf32, fp32 accumulate
+    float acc[kChains][4];
+    unsigned a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = __float_as_uint(1.0f + (float)seed * 1e-3f * (i + 1) + tid * 1e-7f) & 0xffffe000u;
+    b[0] = __float_as_uint(0.5f + (float)seed * 1e-3f) & 0xffffe000u;
+    b[1] = __float_as_uint(0.25f + (float)seed * 1e-3f) & 0xffffe000u;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = (float)i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < kChains; ++i)
+        asm volatile(
+            "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(acc[i][0]), "+f"(acc[i][1]), "+f"(acc[i][2]), "+f"(acc[i][3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += acc[i][0] + acc[i][1] + acc[i][2] + acc[i][3];
+    if (s == 12345.678f) sink[0] = s;
+  } else if (KIND == 14 || KIND == 15) {  // DMMA with a distinct A register per instruction (14) and distinct A and B (15)
     double acc[kChains][2], a[kChains], b[kChains];
 #pragma unroll
     for (int i = 0; i < kChains; ++i) {
@@ -235,6 +256,8 @@ extern "C" int cgp_peak_probe(int32_t kind, double* ops_per_s) {
     // DMMA operand-fetch sensitivity: distinct A (14), distinct A and B (15) per instruction
     case 14: return run_probe<14>(kChains * 8.0, ops_per_s);
     case 15: return run_probe<15>(kChains * 8.0, ops_per_s);
+    // one m16n8k8 mma = 1024 FMAs per warp = 32 per thread
+    case 16: return run_probe<16>(kChains * 32.0, ops_per_s);
     default:
       set_error("unknown probe kind %d", kind);
       return CGP_ERR_BAD_DESC;

@@ -13,7 +13,8 @@ NAMES = {0: "fp64_fma_per_s", 1: "fp32_fma_per_s", 2: "mufu_ex2_per_s", 3: "f64_
          6: "fp64_fma_single_chain_per_s", 7: "fp64_fma_with_int_per_s", 8: "fp64_fma_with_lds_per_s",
          9: "fp64_fma_3_distinct_operands_per_s", 10: "fp64_fma_shared_multiplier_per_s",
          11: "dmma_1chain_1warp_fma_per_s", 12: "dmma_2chain_1warp_fma_per_s", 13: "dmma_4chain_1warp_fma_per_s",
-         14: "dmma_distinct_A_fma_per_s", 15: "dmma_distinct_AB_fma_per_s"}
+         14: "dmma_distinct_A_fma_per_s", 15: "dmma_distinct_AB_fma_per_s",
+         16: "tf32_mma_sync_m16n8k8_fma_per_s"}
 
 
 def probe_all():
