@@ -12,6 +12,7 @@
 #include "fast.cuh"
 #include "kuu_fast.cuh"
 #include "mma64.cuh"
+#include "mma32.cuh"
 #include "generic.cuh"
 
 namespace cgp {
@@ -276,6 +277,24 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
 #define CALL(PH_, PW_)                                                                                   \
   if (nt == 4) return launch_fast(kuf_mma_kernel<PH_, PW_, BWD, 4>, p, tpb_m, smem_m, st, "kuf", unit_m); \
   return launch_fast(kuf_mma_kernel<PH_, PW_, BWD, 2>, p, tpb_m, smem_m, st, "kuf", unit_m)
+    CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+  }
+  static const int use_tc = env_choice(BWD ? "CGP_KUF_BWD_F32" : "CGP_KUF_FWD_F32", 1);  // "mma" | "fma"
+  if constexpr (std::is_same<T, float>::value) if (use_tc) {
+    // float32: 3xTF32 tensor-core kernels
+    static const int nt_env = env_choice("CGP_TF32_TILES", 0);
+    const int nt = nt_env ? nt_env : 4;  // 16-row tiles per warp
+    const int nblk = (g.Pc + 8 * kOctBlock - 1) / (8 * kOctBlock);
+    const int tpb_m = 32 * pick_warps((M + (16 * nt) - 1) / (16 * nt) * 32, 1, 4);
+    const int rows_cta = (tpb_m / 32) * 16 * nt;
+    const int nchunk_m = (M + rows_cta - 1) / rows_cta;
+    p.n_items = (long long)nchunk_m * N * d->C * nblk;
+    const size_t smem_m = mma_smem(p, BWD);
+    const long long unit_m = (long long)d->C * nblk;
+#define CALL(PH_, PW_)                                                                                    \
+  if (nt == 4) return launch_fast(kuf_tf32_kernel<PH_, PW_, BWD, 4>, p, tpb_m, smem_m, st, "kuf", unit_m); \
+  return launch_fast(kuf_tf32_kernel<PH_, PW_, BWD, 2>, p, tpb_m, smem_m, st, "kuf", unit_m)
     CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL
   }
