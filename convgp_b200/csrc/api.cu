@@ -322,7 +322,8 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
   p.ndom = (mode == 2 || p.out_per_channel) ? d->C : 1;
   const int ppd = d->C / p.ndom, Pd = ppd * g.Pc, Hd = ppd * g.Hout;
   static const int use_mma = env_choice(BWD ? "CGP_KDIAG_BWD" : "CGP_KDIAG_FWD", 1);
-  const bool mma_path = std::is_same<T, double>::value && use_mma;
+  static const int use_tc32 = env_choice(BWD ? "CGP_KDIAG_BWD_F32" : "CGP_KDIAG_FWD_F32", 1);
+  const bool mma_path = std::is_same<T, double>::value ? use_mma != 0 : use_tc32 != 0;
   // the MMA kernels hold ~200-250 registers per thread: small CTAs keep several resident per SM
   static const int max_warps_env = env_choice("CGP_KDIAG_WARPS", 0);
   const int max_warps = max_warps_env > 0 ? max_warps_env : (mma_path ? 2 : 8);
@@ -339,6 +340,16 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
     p.n_items = (long long)N * p.ndom * nchunk * p.S;
     const size_t smem_m = mma_smem(p, BWD);
 #define CALL(PH_, PW_) return launch_fast(kdiag_mma_kernel<PH_, PW_, BWD>, p, tpb, smem_m, st, "kdiag")
+    CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+  }
+  if constexpr (std::is_same<T, float>::value) if (mma_path) {
+    const int Lsweep = std::min(Pd, Pd / 2 + 32);
+    const int noct = (Lsweep + 7) / 8;
+    p.S = (noct + kOctBlock - 1) / kOctBlock;
+    p.n_items = (long long)N * p.ndom * nchunk * p.S;
+    const size_t smem_m = mma_smem(p, BWD);
+#define CALL(PH_, PW_) return launch_fast(kdiag_tf32_kernel<PH_, PW_, BWD>, p, tpb, smem_m, st, "kdiag")
     CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL
   }

@@ -391,4 +391,272 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_tf32_kernel(const FastPa
   }
 }
 
+
+// =====================================================================================
+// Kdiag forward / backward, float32 on tensor cores (3xTF32).  Same sweep as kdiag_mma_kernel: a
+// warp owns 32 patches of a pairing domain (two 16-row tiles) and visits the cyclic half range
+// delta = (p' - p) mod Pd in [0, Pd/2] in octets of columns.
+// =====================================================================================
+template <int PH, int PW, bool BWD>
+__global__ void __launch_bounds__(kMaxTPB, 1) kdiag_tf32_kernel(const FastParams<float> p) {
+  using T = float;
+  constexpr int D = PH * PW;
+  constexpr int KS = D / 8, R = D - 8 * KS, KSA = KS ? KS : 1, RA = R ? R : 1;
+  constexpr int NT = 2;  // 32 own patches per warp
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* img = reinterpret_cast<T*>(smem_raw);
+  T* e = img + p.C * p.H * p.Wd;
+  const int nW = p.w_per_plane ? p.C * p.Pc : p.Pc;
+  T* w = e + p.C * p.Pc;
+  T* dWacc = w + nW;
+  T* red = dWacc + (BWD ? nW : 0);
+  int* org = reinterpret_cast<int*>(red + 32);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const bool do_dw = BWD && p.dW != nullptr;
+  for (int i = tid; i < nW; i += blockDim.x) {
+    w[i] = p.Wt ? p.Wt[i] : T(1);
+    if (BWD) dWacc[i] = T(0);
+  }
+  for (int i = tid; i < p.C * p.Pc; i += blockDim.x) {
+    const int cp = i / p.Pc, pp = i - cp * p.Pc;
+    org[i] = cp * p.H * p.Wd + (pp / p.Wout) * p.Wd + (pp % p.Wout);
+  }
+  __syncthreads();
+
+  int offb[KSA][2], offr[RA];
+#pragma unroll
+  for (int s = 0; s < KS; ++s) {
+    offb[s][0] = elem_off<PH, PW>(8 * s + t4, p.Wd);
+    offb[s][1] = elem_off<PH, PW>(8 * s + t4 + 4, p.Wd);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) offr[r] = elem_off<PH, PW>(8 * KS + r, p.Wd);
+
+  const long long lo = p.n_items * blockIdx.x / gridDim.x;
+  const long long hi = p.n_items * (blockIdx.x + 1) / gridDim.x;
+  const int ndom = p.ndom, ppd = p.C / ndom, Pd = ppd * p.Pc;
+  const int nchunk = (Pd + blockDim.x - 1) / blockDim.x;
+  const int half = Pd / 2;
+  const bool even = (Pd & 1) == 0;
+  const int Lsweep = min(Pd, half + 32);
+  const T P2 = (T)(p.Pn * p.Pn);
+
+  unsigned ahi[NT][KSA][4], alo[NT][KSA][4];
+  T ar[NT][2][RA], em[NT][2], wown[NT][2], acc[NT][2], acc2[NT][2], dwown[NT][2];
+  int own[NT][2];
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      acc[t][h] = acc2[t][h] = dwown[t][h] = em[t][h] = wown[t][h] = T(0);
+      own[t][h] = 0;
+    }
+  int cur_key = -1, cur_img = -1, kn = 0, kdm = 0;
+  T sig2 = T(0), lsg = T(1);
+
+  auto flush = [&]() {
+    const int gi = p.grp_per_plane ? kdm : 0;
+    const size_t o = p.out_per_channel ? (size_t)kn * p.C + kdm : (size_t)kn;
+    const int cb = (ndom == 1) ? 0 : kdm;
+    T v = T(0), v2 = T(0);
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        v = fmaf(wown[t][h], acc[t][h], v);
+        v2 = fmaf(wown[t][h], acc2[t][h], v2);
+      }
+    if constexpr (!BWD) {
+      v = block_sum(v, red);
+      if (tid == 0) atomicAdd(p.out + o, v * sig2 / P2);
+    } else {
+      const T gn = p.G[o] / P2;
+      v = block_sum(v, red);
+      v2 = block_sum(v2, red);
+      if (tid == 0) {
+        if (p.dvar) atomicAdd(p.dvar + gi, gn * v);
+        if (p.dls) atomicAdd(p.dls + gi, T(-2) * sig2 / lsg * gn * v2 / Math<T>::kArgScale);
+      }
+      if (do_dw) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const T dsum = quad_sum(dwown[t][h]);
+            if (t4 == 0 && own[t][h] < Pd)
+              atomicAdd(dWacc + (p.w_per_plane ? cb * p.Pc : 0) + own[t][h], T(2) * sig2 * gn * dsum);
+          }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) acc[t][h] = acc2[t][h] = dwown[t][h] = T(0);
+  };
+
+  int blk, j, dm, n;
+  {
+    long long tt = lo;
+    blk = (int)(tt % p.S);
+    tt /= p.S;
+    j = (int)(tt % nchunk);
+    tt /= nchunk;
+    dm = (int)(tt % ndom);
+    n = (int)(tt / ndom);
+  }
+  for (long long it = lo; it < hi; ++it, ++blk) {
+    if (blk == p.S) {
+      blk = 0;
+      if (++j == nchunk) {
+        j = 0;
+        if (++dm == ndom) {
+          dm = 0;
+          ++n;
+        }
+      }
+    }
+    const int cb = (ndom == 1) ? 0 : dm;
+    const int key = (n * ndom + dm) * nchunk + j;
+    const int wbase = j * blockDim.x + warp * 32;
+    if (key != cur_key) {
+      if (cur_key >= 0) flush();
+      if (n != cur_img) {
+        __syncthreads();
+        stage_image<T, PH, PW>(p, n, img, e);
+        cur_img = n;
+      }
+      cur_key = key;
+      kn = n;
+      kdm = dm;
+      const int gi = p.grp_per_plane ? dm : 0;
+      sig2 = p.var[gi];
+      lsg = p.ls[gi];
+      const T sc = Math<T>::kArgScale / (lsg * lsg);
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          own[t][h] = wbase + 16 * t + 8 * h + g;
+          const bool act = own[t][h] < Pd;
+          const T* base = img + org[cb * p.Pc + (act ? own[t][h] : 0)];
+#pragma unroll
+          for (int s = 0; s < KS; ++s)
+#pragma unroll
+            for (int x = 0; x < 2; ++x)
+              tf32_split(act ? base[offb[s][x]] * sc : T(0), ahi[t][s][h + 2 * x], alo[t][s][h + 2 * x]);
+#pragma unroll
+          for (int r = 0; r < R; ++r) ar[t][h][r] = act ? base[offr[r]] * sc : T(0);
+          em[t][h] = act ? e[cb * p.Pc + own[t][h]] : T(0);
+          wown[t][h] = act ? w[(p.w_per_plane ? cb * p.Pc : 0) + own[t][h]] : T(0);
+        }
+    }
+    if (wbase >= Pd) continue;
+    const T* ep = e + cb * p.Pc;
+    const int* orgc = org + cb * p.Pc;
+    const int woff = p.w_per_plane ? cb * p.Pc : 0;
+    const T* wp = w + woff;
+    T gs = T(0);
+    if constexpr (BWD) {
+      const size_t o = p.out_per_channel ? (size_t)n * p.C + dm : (size_t)n;
+      gs = T(2) * sig2 * p.G[o] / P2;
+    }
+    auto octet = [&](int v0i, auto interior_c) {
+      constexpr bool INT = decltype(interior_c)::value;
+      int pB = wbase + (INT ? v0i + g : min(v0i + g, Lsweep - 1));
+      pB -= pB >= Pd ? Pd : 0;
+      const T* bB = img + orgc[pB];
+      const int vi0 = v0i + 2 * t4, vi1 = vi0 + 1;
+      const bool c0 = INT || vi0 < Lsweep, c1 = INT || vi1 < Lsweep;
+      int q0 = wbase + (INT ? vi0 : min(vi0, Lsweep - 1)), q1 = wbase + (INT ? vi1 : min(vi1, Lsweep - 1));
+      q0 -= q0 >= Pd ? Pd : 0;
+      q1 -= q1 >= Pd ? Pd : 0;
+      const T e0 = ep[q0], e1 = ep[q1];
+      T cf[NT][4];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        cf[t][0] = em[t][0] + e0;
+        cf[t][1] = em[t][0] + e1;
+        cf[t][2] = em[t][1] + e0;
+        cf[t][3] = em[t][1] + e1;
+      }
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        unsigned bh0, bl0, bh1, bl1;
+        tf32_split(bB[offb[s][0]], bh0, bl0);
+        tf32_split(bB[offb[s][1]], bh1, bl1);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) hmma_3x(cf[t], ahi[t][s], alo[t][s], bh0, bh1, bl0, bl1);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const T x0 = img[orgc[q0] + offr[r]], x1 = img[orgc[q1] + offr[r]];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          cf[t][0] = fmaf(ar[t][0][r], x0, cf[t][0]);
+          cf[t][1] = fmaf(ar[t][0][r], x1, cf[t][1]);
+          cf[t][2] = fmaf(ar[t][1][r], x0, cf[t][2]);
+          cf[t][3] = fmaf(ar[t][1][r], x1, cf[t][3]);
+        }
+      }
+      const T w0 = c0 ? wp[q0] : T(0), w1 = c1 ? wp[q1] : T(0);
+      T sc0 = T(0), sc1 = T(0);
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          int wt0 = 2, wt1 = 2;
+          if constexpr (!INT) {
+            int d0 = q0 - own[t][h], d1 = q1 - own[t][h];
+            d0 += d0 < 0 ? Pd : 0;
+            d1 += d1 < 0 ? Pd : 0;
+            wt0 = d0 == 0 ? 1 : (d0 < half || (!even && d0 == half)) ? 2 : (even && d0 == half) ? 1 : 0;
+            wt1 = d1 == 0 ? 1 : (d1 < half || (!even && d1 == half)) ? 2 : (even && d1 == half) ? 1 : 0;
+            if (!c0 || own[t][h] >= Pd) wt0 = 0;
+            if (!c1 || own[t][h] >= Pd) wt1 = 0;
+          }
+          const T a0 = wt0 ? cf[t][2 * h] : T(0), a1 = wt1 ? cf[t][2 * h + 1] : T(0);
+          const T k0 = Math<T>::exp_arg(a0, nullptr), k1 = Math<T>::exp_arg(a1, nullptr);
+          const T wk0 = w0 * k0, wk1 = w1 * k1;
+          acc[t][h] = fmaf((T)wt0, wk0, acc[t][h]);
+          acc[t][h] = fmaf((T)wt1, wk1, acc[t][h]);
+          if constexpr (BWD) {
+            acc2[t][h] = fmaf((T)wt0 * wk0, a0, acc2[t][h]);
+            acc2[t][h] = fmaf((T)wt1 * wk1, a1, acc2[t][h]);
+            dwown[t][h] += (wt0 ? wk0 : T(0)) + (wt1 ? wk1 : T(0));
+            sc0 = fmaf(wt0 == 2 ? wown[t][h] : T(0), k0, sc0);
+            sc1 = fmaf(wt1 == 2 ? wown[t][h] : T(0), k1, sc1);
+          }
+        }
+      if constexpr (BWD) {
+        if (do_dw) {
+          sc0 = rows_sum(sc0);
+          sc1 = rows_sum(sc1);
+          if (g == 0) {
+            if (c0) atomicAdd(dWacc + woff + q0, sc0 * gs);
+            if (c1) atomicAdd(dWacc + woff + q1, sc1 * gs);
+          }
+        }
+      }
+    };
+    const bool warp_full = wbase + 31 < Pd;
+#pragma unroll
+    for (int ob = 0; ob < kOctBlock; ++ob) {
+      const int v0i = (blk * kOctBlock + ob) * 8;
+      if (v0i >= Lsweep) continue;
+      if (warp_full && v0i >= 32 && v0i + 7 < half && v0i + 7 < Lsweep) octet(v0i, std::true_type{});
+      else octet(v0i, std::false_type{});
+    }
+  }
+  if (cur_key >= 0) flush();
+  if (do_dw) {
+    __syncthreads();
+    for (int i = tid; i < nW; i += blockDim.x) {
+      T v = dWacc[i];
+      if (v != T(0)) atomicAdd(p.dW + i, v);
+    }
+  }
+}
+
 }  // namespace cgp

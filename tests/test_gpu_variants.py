@@ -1,5 +1,6 @@
-"""Both float64 kernel families (FP64-MMA and scalar-FMA) must pass parity whatever the library's
-default selection is: re-run the f64 parity + golden tests in subprocesses with the selection forced."""
+"""Both kernel families of each dtype (float64: FP64-MMA / scalar FMA; float32: 3xTF32 tensor-core /
+scalar FMA) must pass parity whatever the library's default selection is: re-run the parity, golden
+and identity tests in subprocesses with the selection forced."""
 import os
 import subprocess
 import sys
@@ -15,7 +16,8 @@ def test_forced_kernel_family(family):
     env = dict(os.environ)
     for k in ("CGP_KUF_FWD", "CGP_KUF_BWD", "CGP_KDIAG_FWD", "CGP_KDIAG_BWD"):
         env[k] = family
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-k", "f64", "tests/test_gpu_parity.py",
+        env[k + "_F32"] = family
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "tests/test_gpu_parity.py",
                         "tests/test_golden.py", "tests/test_gpu_identities.py", "-p", "no:cacheprovider"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
