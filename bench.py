@@ -226,7 +226,7 @@ def run_gpu(args):
     import ctypes
     peaks = {}
     if rank == 0:
-        for kind, name in ((0, "fp64_fma"), (1, "fp32_fma"), (2, "mufu_ex2"), (3, "f64_exp"), (4, "fp64_mma")):
+        for kind, name in ((0, "fp64_fma"), (1, "fp32_fma"), (2, "mufu_ex2"), (3, "f64_exp"), (4, "fp64_mma"), (16, "tf32_mma")):
             v = ctypes.c_double()
             _lib.check(_lib.lib().cgp_peak_probe(kind, ctypes.byref(v)))
             peaks[name] = v.value
@@ -404,9 +404,12 @@ def run_gpu(args):
         pipe, peak_note = "fp64", ("FP64 pipe: flops/(2*max(DFMA, DMMA) rate) + exps/(library exp rate), all probed on "
                                    "this GPU by cgp_peak_probe (MEASURED_PEAKS.json has no FP64 figure)")
     else:
+        fma32 = max(peaks["fp32_fma"], peaks["tf32_mma"] / 3.0)  # 3xTF32 split: three MMAs per float32 product
+
         def t_bound(fl, ex):
-            return max(fl / (2 * peaks["fp32_fma"]), ex / peaks["mufu_ex2"])
-        pipe, peak_note = "fp32", "max(FP32 FMA pipe, MUFU ex2 pipe), both probed on this GPU"
+            return max(fl / (2 * fma32), ex / peaks["mufu_ex2"])
+        pipe, peak_note = "fp32", ("max(flops/(2*max(FFMA, TF32 mma.sync/3) rate), exps/MUFU ex2 rate), all probed on "
+                                   "this GPU by cgp_peak_probe")
     dom = max(per_kernel, key=per_kernel.get)
     fl, ex = work[dom]
     dur = per_kernel[dom] * 1e-3

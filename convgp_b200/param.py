@@ -37,11 +37,16 @@ class LowerTriangular:
     def __init__(self, M, L):
         self.M, self.L = M, L
         self._idx = np.tril_indices(M)
+        self._dev_idx = {}
 
     def forward(self, x):
         out = torch.zeros(self.M, self.M, self.L, dtype=x.dtype, device=x.device)
-        r, c = self._idx
-        out[torch.as_tensor(r, device=x.device), torch.as_tensor(c, device=x.device), :] = x.view(-1, self.L)
+        key = str(x.device)
+        if key not in self._dev_idx:  # index tensors live on the device: no H2D copy per evaluation
+            r, c = self._idx
+            self._dev_idx[key] = (torch.as_tensor(r, device=x.device), torch.as_tensor(c, device=x.device))
+        r, c = self._dev_idx[key]
+        out[r, c, :] = x.view(-1, self.L)
         return out
 
     def backward(self, y):

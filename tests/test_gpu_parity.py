@@ -37,6 +37,11 @@ def cases():
              [(1.0, 1.0, None, False), (0.5, 0.7, S3[0:3], False), (0.6, 0.9, S3[3:6], False),
               (0.7, 1.1, S3[0:7:3], False), (0.4, np.array([0.9, 1.2, 1.5]), S3[2:9:3], True)], N=3, M=10),
         Case("multi_generic", "multi", 9, 9, 2, 4, 4, rbf(1.2, 1.1), N=3, M=8),
+        # --- edge shapes: a single patch per image, single image / inducing patch, ragged tile counts
+        Case("one_patch", "conv", 5, 5, 1, 5, 5, rbf(0.9, 2.0), N=2, M=3),
+        Case("m1_n1", "conv", 7, 7, 1, 3, 3, rbf(1.1, 1.3), N=1, M=1),
+        Case("ragged_m33_p35", "conv", 9, 7, 1, 3, 3, rbf(0.8, 1.2), N=3, M=33),
+        Case("ragged_c2_m17", "conv", 6, 9, 2, 2, 2, rbf(1.0, 0.9), N=2, M=17),
     ]
 
 
@@ -148,3 +153,17 @@ def test_full_size_cifar_shapes_f64(idx):
                                case.name + "_subsample.npz"))
     assert rel_err(kuf[::25, ::2], sub["kuf"]) < 1e-10
     assert rel_err(kd, sub["kdiag"]) < 1e-10
+
+
+def test_empty_batch_and_empty_inducing_set():
+    """N = 0 and M = 0 are legal (the reference's reshape-based code handles them implicitly)."""
+    from convgp_b200 import convkernels as ck, kernels as bk
+    from convgp_b200.kernels import as_tensor
+    k = ck.WeightedConv(bk.RBF(25), [28, 28], [5, 5])
+    X0 = as_tensor(np.zeros((0, 784)))
+    Z = as_tensor(np.random.RandomState(0).rand(4, 25))
+    assert tuple(k.Kzx(Z, X0).shape) == (4, 0)
+    assert tuple(k.Kdiag(X0).shape) == (0,)
+    X = as_tensor(np.random.RandomState(1).rand(3, 784))
+    assert tuple(k.Kzx(Z[:0], X).shape) == (0, 3)
+    assert tuple(k.Kzz(Z[:0]).shape) == (0, 0)

@@ -53,7 +53,8 @@ class Case:
         g = self.geom
         # Z: patches of X + small noise (mirrors init_inducing, convkernels.py:93-97)
         opat = self.oracle_kernel(np.ones(self.wshape()))._get_patches(self.X).reshape(-1, g.D)
-        self.Z = opat[rng.permutation(len(opat))[:M]] + 0.001 * rng.rand(M, g.D)
+        sel = opat[rng.permutation(len(opat))[:M]]
+        self.Z = sel + 0.001 * rng.rand(M, g.D)[:len(sel)]
         if len(self.Z) < M:
             self.Z = np.concatenate([self.Z, rng.rand(M - len(self.Z), g.D)])
         self.Wv = rng.randn(*self.wshape()) if weighted else None
