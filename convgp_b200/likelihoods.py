@@ -8,9 +8,17 @@ import torch
 from .param import Param, Parameterized, Positive
 
 
+_GH_CACHE = {}
+
+
 def _gh(n, dtype, device):
-    x, w = np.polynomial.hermite.hermgauss(n)
-    return torch.as_tensor(x, dtype=dtype, device=device), torch.as_tensor(w, dtype=dtype, device=device)
+    """Gauss-Hermite nodes / weights as device tensors (cached: no host-to-device copy per evaluation,
+    which also keeps the ELBO capturable in a CUDA graph)."""
+    key = (n, dtype, str(device))
+    if key not in _GH_CACHE:
+        x, w = np.polynomial.hermite.hermgauss(n)
+        _GH_CACHE[key] = (torch.as_tensor(x, dtype=dtype, device=device), torch.as_tensor(w, dtype=dtype, device=device))
+    return _GH_CACHE[key]
 
 
 def _probit(x):
@@ -103,7 +111,9 @@ class MultiClass(Likelihood):
         cdfs = 0.5 * (1.0 + torch.erf(dist / np.sqrt(2.0)))
         cdfs = cdfs * (1 - 2e-4) + 1e-4
         cdfs = cdfs * (1.0 - oh_on)[:, :, None] + oh_on[:, :, None]
-        return torch.prod(cdfs, dim=1) @ (gw / np.sqrt(np.pi))[:, None]
+        # product over classes as exp(sum(log)): every factor is >= 1e-4, and -- unlike torch.prod, whose
+        # backward counts zeros with a host sync -- this stays capturable in a CUDA graph
+        return torch.exp(torch.log(cdfs).sum(dim=1)) @ (gw / np.sqrt(np.pi))[:, None]
 
     def variational_expectations(self, Fmu, Fvar, Y):
         p = self._prob_is_largest(Y, Fmu, Fvar)

@@ -38,6 +38,9 @@ def conditional(Xnew, X, Kdiag, Kmn, Kmm, f, full_cov=False, q_sqrt=None, whiten
     if full_cov:
         raise NotImplementedError("full_cov needs K(Xnew, Xnew), which this entry point is not given "
                                   "(the reference's own branch is `None - A^T A`, misvgp.py:135)")
+    if whiten and q_sqrt is not None and q_sqrt.dim() == 3 and Kmn.is_cuda:
+        from .conditional import whitened_conditional  # the case every script runs: one fused autograd node
+        return whitened_conditional(Kdiag, Kmn, Kmm, f, q_sqrt)
     num_func = f.shape[1]
     Lm = torch.linalg.cholesky(Kmm)  # :128
     A = torch.linalg.solve_triangular(Lm, Kmn, upper=False)  # :131

@@ -9,6 +9,7 @@ class _Settings:
     def __init__(self):
         self.float_type = torch.float64
         self.jitter_level = 1e-5  # gpflowrc:11
+        self.check_cholesky = True  # raise on a non-PD Kmm (costs one host sync per step; off inside CUDA graphs)
         self._device = None
 
     @property

@@ -179,3 +179,36 @@ def test_svconvgp_matches_patch_level_bruteforce():
     assert rel_err(mu, omu) < 1e-7 and rel_err(var, ovar) < 1e-7
     pp = m.compute_patch_predictions(X)
     assert pp.shape == (N, 36, L) and rel_err(pp.sum(1), omu) < 1e-7
+
+
+def test_graphed_objective_matches_eager_and_non_pd_raises():
+    ck, bk, lik, _, svgp, _, _ = _pkg()
+    from convgp_b200 import _lib
+    rng = np.random.RandomState(6)
+    N, M, L = 40, 9, 3
+    X, Y = _data(rng, N, 100, classes=L)
+    k = ck.WeightedConv(bk.RBF(9, variance=0.8, lengthscales=1.4), [10, 10], [3, 3]) + bk.White(1, 1e-3)
+    Z = O.WeightedConv(O.RBF(9, 0.8, 1.4), [10, 10], [3, 3]).init_inducing(X, M, rng=rng)
+    m = svgp.SVGP(X, Y, k, lik.MultiClass(L), Z, num_latent=L, minibatch_size=16)
+    q_mu, q_sqrt = _variational(rng, M, L)
+    m.q_mu, m.q_sqrt = q_mu, q_sqrt
+    x0 = m.get_free_state()
+    m._rng = np.random.RandomState(11)
+    step = m.graphed_objective()
+    m._rng = np.random.RandomState(12)
+    flat = step().double().cpu().numpy()
+    m._mb_idx = None  # back to eager minibatching with the same random stream
+    m._rng = np.random.RandomState(12)
+    f, g = m._objective(x0)
+    assert abs(flat[0] - f) < 1e-9 * abs(f)
+    assert rel_err(flat[1:], g) < 1e-9
+    # a non-PD Kmm raises (TF would), with the pivot index in the message
+    from convgp_b200.conditional import whitened_conditional
+    import torch
+    bad = -torch.eye(4, dtype=torch.float64, device="cuda")
+    with pytest.raises(_lib.CgpError) as e:
+        whitened_conditional(torch.ones(3, dtype=torch.float64, device="cuda"),
+                             torch.ones(4, 3, dtype=torch.float64, device="cuda"), bad,
+                             torch.zeros(4, 2, dtype=torch.float64, device="cuda"),
+                             torch.eye(4, dtype=torch.float64, device="cuda")[:, :, None].repeat(1, 1, 2))
+    assert e.value.status == -6

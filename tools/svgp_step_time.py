@@ -33,3 +33,13 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(3): step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=60))
+
+# ---- the same step replayed from a CUDA graph
+m2 = svgp.SVGP(X, Y, k, lik.MultiClass(L), inp["Z"], num_latent=L)
+gstep = m2.graphed_objective()
+for _ in range(3): gstep()
+torch.cuda.synchronize()
+a.record()
+for _ in range(20): gstep()
+b.record(); torch.cuda.synchronize()
+print("graphed SVGP step ms:", a.elapsed_time(b) / 20)
