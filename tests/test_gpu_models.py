@@ -212,3 +212,19 @@ def test_graphed_objective_matches_eager_and_non_pd_raises():
                              torch.zeros(4, 2, dtype=torch.float64, device="cuda"),
                              torch.eye(4, dtype=torch.float64, device="cuda")[:, :, None].repeat(1, 1, 2))
     assert e.value.status == -6
+
+
+def test_predict_batched_matches_predict_y():
+    ck, bk, lik, _, svgp, _, _ = _pkg()
+    rng = np.random.RandomState(8)
+    N, M, L = 37, 9, 3
+    X, Y = _data(rng, N, 100, classes=L)
+    k = ck.WeightedConv(bk.RBF(9, variance=0.8, lengthscales=1.4), [10, 10], [3, 3]) + bk.White(1, 1e-3)
+    Z = O.WeightedConv(O.RBF(9, 0.8, 1.4), [10, 10], [3, 3]).init_inducing(X, M, rng=rng)
+    m = svgp.SVGP(X, Y, k, lik.MultiClass(L), Z, num_latent=L)
+    m.q_mu, m.q_sqrt = _variational(rng, M, L)
+    py, pv = m.predict_y(X)
+    by, bv = m.predict_batched(X, batch_size=10)
+    assert rel_err(by, py) < 1e-10 and rel_err(bv, pv) < 1e-10
+    dens = m.predict_batched(X, batch_size=16, density_Y=Y)
+    assert rel_err(dens, m.predict_density(X, Y)) < 1e-10
