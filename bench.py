@@ -232,7 +232,7 @@ def run_gpu(args):
             peaks[name] = v.value
 
     if not args.no_graph:
-        hp.capture()
+        hp.capture(overlapped=True)  # Kuf / Kdiag / Kuu of each phase on parallel graph branches
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
         hp.step()
@@ -441,7 +441,7 @@ def run_gpu(args):
         "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": WORKLOAD, "images_per_gpu_per_step": N_BATCH, "M": M_IND,
                    "l2": "256 MB buffer written between timed steps (inputs are ~5 MB, far below the 126 MB L2)",
-                   "cuda_graph": not args.no_graph,
+                   "cuda_graph": not args.no_graph, "graph_branches": "Kuf | Kdiag | Kuu of each phase run on parallel branches",
                    "collective": "NCCL all-reduce of the packed gradient buffer per step" if world > 1 else "none"},
         "roofline": {
             "bound": pipe, "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

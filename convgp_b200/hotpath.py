@@ -5,6 +5,8 @@ This is what a data-parallel rank runs per step: its shard of the minibatch rows
 parameters, and ONE packed gradient buffer [dZ | dW | dvariance | dlengthscales] that the NCCL
 all-reduce sums across ranks.  ``step()`` is stream-ordered and allocation-free, so
 it can be captured in a CUDA graph (``capture()``)."""
+import ctypes  # noqa: F401
+
 import torch
 
 from . import _lib
@@ -58,6 +60,42 @@ class HotPath:
         check(L.cgp_kuu_bwd(s.ref(), self.M, ptr(self.Z), ptr(self.variance), ptr(self.lengthscales), ptr(self.Gu),
                             ptr(self.dZ), ptr(self.dvar), ptr(self.dls), st))
 
+    def step_overlapped(self):
+        """forward+backward with the three independent kernels of each phase on three streams
+        (fork/join with events): every kernel is a persistent grid that fills the GPU, so the gain
+        is the overlap of one kernel's ramp-up / tail with another's body.  Capturable."""
+        L, s = _lib.lib(), self.spec
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_side"):
+            self._side = [torch.cuda.Stream(), torch.cuda.Stream()]
+        s1, s2 = self._side
+        sp = lambda st: _lib.ctypes.c_void_p(st.cuda_stream)  # noqa: E731
+        self.grads.zero_()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        s1.wait_event(fork)
+        s2.wait_event(fork)
+        # forward
+        check(L.cgp_kuf_fwd(s.ref(), self.N, self.M, ptr(self.X), ptr(self.Z), ptr(self.W), ptr(self.variance),
+                            ptr(self.lengthscales), ptr(self.Kuf), ptr(self.ws), self.ws_bytes, sp(main)))
+        check(L.cgp_kdiag_fwd(s.ref(), self.N, ptr(self.X), ptr(self.W), ptr(self.variance), ptr(self.lengthscales),
+                              ptr(self.Kdiag), ptr(self.ws), self.ws_bytes, sp(s1)))
+        check(L.cgp_kuu_fwd(s.ref(), self.M, ptr(self.Z), ptr(self.variance), ptr(self.lengthscales), self.diag_add,
+                            ptr(self.Kuu), sp(s2)))
+        # backward (all three accumulate atomically into the packed gradient buffer)
+        check(L.cgp_kuf_bwd(s.ref(), self.N, self.M, ptr(self.X), ptr(self.Z), ptr(self.W), ptr(self.variance),
+                            ptr(self.lengthscales), ptr(self.G), ptr(self.dZ), ptr(self.dW), ptr(self.dvar),
+                            ptr(self.dls), ptr(self.ws), self.ws_bytes, sp(main)))
+        check(L.cgp_kdiag_bwd(s.ref(), self.N, ptr(self.X), ptr(self.W), ptr(self.variance), ptr(self.lengthscales),
+                              ptr(self.gd), ptr(self.dW), ptr(self.dvar), ptr(self.dls), ptr(self.ws),
+                              self.ws_bytes, sp(s1)))
+        check(L.cgp_kuu_bwd(s.ref(), self.M, ptr(self.Z), ptr(self.variance), ptr(self.lengthscales), ptr(self.Gu),
+                            ptr(self.dZ), ptr(self.dvar), ptr(self.dls), sp(s2)))
+        for st in (s1, s2):
+            j = torch.cuda.Event()
+            j.record(st)
+            main.wait_event(j)
+
     def step(self):
         if self.graph is not None:
             self.graph.replay()
@@ -65,15 +103,20 @@ class HotPath:
             self.forward()
             self.backward()
 
-    def capture(self):
+    def capture(self, overlapped=False):
         """Capture forward+backward into a CUDA graph (launch-latency matters: the whole step is
-        ~1 ms of GPU time at the MNIST shape)."""
+        ~1 ms of GPU time at the MNIST shape).  overlapped=True captures the three-stream variant."""
         self.forward()
         self.backward()
+        if overlapped:
+            self.step_overlapped()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.forward()
-            self.backward()
+            if overlapped:
+                self.step_overlapped()
+            else:
+                self.forward()
+                self.backward()
         self.graph = g
         return g
