@@ -13,6 +13,7 @@
 #include "kuu_fast.cuh"
 #include "mma64.cuh"
 #include "mma32.cuh"
+#include "umma32.cuh"
 #include "generic.cuh"
 
 namespace cgp {
@@ -164,6 +165,7 @@ static size_t fast_smem(const FastParams<T>& p, int tpb, bool bwd) {
 static int env_choice(const char* name, int dflt) {
   const char* v = getenv(name);
   if (!v) return dflt;
+  if (!strcmp(v, "umma")) return 2;
   if (!strcmp(v, "mma")) return 1;
   if (!strcmp(v, "fma")) return 0;
   return atoi(v);
@@ -249,6 +251,63 @@ static int launch_fast(K kernel, P& p, int tpb, size_t smem, cudaStream_t st, co
   else if (ph == 2 && pw == 2) { CALL(2, 2); }          \
   else { set_error("no specialised kernel for %dx%d patches", ph, pw); return CGP_ERR_UNSUPPORTED; }
 
+// ---- float32 tcgen05 (UMMA) family: single-channel images, one RBF over the whole patch -------------
+static bool umma_ok(const cgp_kernel_desc* d, const Geo& g, int mode) {
+  if (mode != 1 || d->C != 1 || d->dtype != CGP_F32) return false;
+  const int KP = umma::pad_k(g.D);
+  return umma::smem_plan(KP, d->H * d->W, g.P).total <= 227 * 1024;
+}
+
+// mode: 0 Kuf fwd, 1 Kdiag fwd, 2 Kdiag bwd, 3 dW of Kuf (umma32.cuh)
+static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int N, int M, const void* X,
+                           const void* Z, const void* W, const void* var, const void* ls, const void* G, void* out,
+                           void* dW, void* dvar, void* dls, cudaStream_t st) {
+  umma::Params p;
+  memset(&p, 0, sizeof(p));
+  p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
+  p.ls = (const float*)ls; p.G = (const float*)G; p.out = (float*)out; p.dW = (float*)dW;
+  p.dvar = (float*)dvar; p.dls = (float*)dls;
+  p.N = N; p.M = M; p.H = d->H; p.Wd = d->W; p.Hout = g.Hout; p.Wout = g.Wout; p.P = g.P; p.D = g.D;
+  p.mode = mode;
+  p.Pn = (float)g.P;
+  const int p_rt = (g.P + umma::TM - 1) / umma::TM, p_ct = (g.P + umma::TN - 1) / umma::TN;
+  if (mode == 0) {
+    p.E1 = N; p.E2 = p_ct;
+    p.n_units = (long long)((M + umma::TM - 1) / umma::TM) * N * p_ct;
+  } else if (mode == 3) {
+    p.E1 = N; p.E2 = p_rt;
+    p.n_units = (long long)((M + umma::TN - 1) / umma::TN) * N * p_rt;
+  } else {
+    p.E1 = p_rt; p.E2 = p_ct;
+    p.n_units = (long long)N * p_rt * p_ct;
+  }
+  if (p.n_units < 1) return CGP_OK;
+  const size_t smem = umma::smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total;
+  // one persistent CTA per SM; a CTA never gets less than one whole row group, so every output
+  // element receives at most two atomic contributions (order-independent sums)
+  const long long group = mode == 3 ? 1 : p.E2;
+  const long long grid = std::max<long long>(1, std::min<long long>(p.n_units / group, num_sms()));
+  int dev = 0;
+  CGP_CUDA_CHECK(cudaGetDevice(&dev));
+#define CALL(PH_, PW_)                                                                                        \
+  {                                                                                                           \
+    auto kernel = mode == 2 ? umma::rowsum_kernel<PH_, PW_, true> : umma::rowsum_kernel<PH_, PW_, false>;     \
+    {                                                                                                         \
+      std::lock_guard<std::mutex> lk(g_launch_mu);                                                            \
+      size_t& cur = g_launch_smem[std::make_pair((const void*)kernel, dev)];                                  \
+      if (smem > cur) {                                                                                       \
+        CGP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        cur = smem;                                                                                           \
+      }                                                                                                       \
+    }                                                                                                         \
+    kernel<<<(unsigned)grid, umma::kThreads, smem, st>>>(p);                                                  \
+    CGP_CUDA_CHECK(cudaGetLastError());                                                                       \
+    return CGP_OK;                                                                                            \
+  }
+  CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+}
+
 template <typename T, bool BWD>
 static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N, int M, const void* X,
                         const void* Z, const void* W, const void* var, const void* ls, const void* G, void* out,
@@ -262,6 +321,11 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
   if (!BWD) {
     size_t bytes = sizeof(T) * (size_t)M * N * (p.out_per_channel ? d->C : 1);
     CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
+  }
+  if constexpr (std::is_same<T, float>::value) {
+    static const int fam = env_choice(BWD ? "CGP_KUF_BWD_F32" : "CGP_KUF_FWD_F32", 2);  // "umma" | "mma" | "fma"
+    if (fam == 2 && !BWD && umma_ok(d, g, mode))
+      return run_umma_rowsum(0, d, g, N, M, X, Z, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st);
   }
   static const int use_mma = env_choice(BWD ? "CGP_KUF_BWD" : "CGP_KUF_FWD", 1);
   if constexpr (std::is_same<T, double>::value) if (use_mma) {
@@ -280,7 +344,7 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL
   }
-  static const int use_tc = env_choice(BWD ? "CGP_KUF_BWD_F32" : "CGP_KUF_FWD_F32", 1);  // "mma" | "fma"
+  static const int use_tc = env_choice(BWD ? "CGP_KUF_BWD_F32" : "CGP_KUF_FWD_F32", 2);  // "umma" | "mma" | "fma"
   if constexpr (std::is_same<T, float>::value) if (use_tc) {
     // float32: 3xTF32 tensor-core kernels
     static const int nt_env = env_choice("CGP_TF32_TILES", 0);
@@ -322,7 +386,7 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
   p.ndom = (mode == 2 || p.out_per_channel) ? d->C : 1;
   const int ppd = d->C / p.ndom, Pd = ppd * g.Pc, Hd = ppd * g.Hout;
   static const int use_mma = env_choice(BWD ? "CGP_KDIAG_BWD" : "CGP_KDIAG_FWD", 1);
-  static const int use_tc32 = env_choice(BWD ? "CGP_KDIAG_BWD_F32" : "CGP_KDIAG_FWD_F32", 1);
+  static const int use_tc32 = env_choice(BWD ? "CGP_KDIAG_BWD_F32" : "CGP_KDIAG_FWD_F32", 2);
   const bool mma_path = std::is_same<T, double>::value ? use_mma != 0 : use_tc32 != 0;
   // the MMA kernels hold ~200-250 registers per thread: small CTAs keep several resident per SM
   static const int max_warps_env = env_choice("CGP_KDIAG_WARPS", 0);
@@ -332,6 +396,10 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
   if (!BWD) {
     size_t bytes = sizeof(T) * (size_t)N * (p.out_per_channel ? d->C : 1);
     CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
+  }
+  if constexpr (std::is_same<T, float>::value) {
+    if (use_tc32 == 2 && umma_ok(d, g, mode))
+      return run_umma_rowsum(BWD ? 2 : 1, d, g, N, 0, X, nullptr, W, var, ls, G, out, dW, dvar, dls, st);
   }
   if constexpr (std::is_same<T, double>::value) if (mma_path) {
     const int Lsweep = std::min(Pd, Pd / 2 + 32);
