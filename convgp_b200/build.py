@@ -9,7 +9,7 @@ LIB = os.path.join(HERE, "libconvgp_b200.so")
 SOURCES = ["api.cu", "probe.cu"]
 HEADERS = ["common.cuh", "fast.cuh", "kuu_fast.cuh", "mma64.cuh", "mma32.cuh", "umma32.cuh", "generic.cuh", os.path.join("..", "..", "include", "convgp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("CGP_NVCC_EXTRA", "").split()
 
 
 def _stale():

@@ -251,11 +251,14 @@ static int launch_fast(K kernel, P& p, int tpb, size_t smem, cudaStream_t st, co
   else if (ph == 2 && pw == 2) { CALL(2, 2); }          \
   else { set_error("no specialised kernel for %dx%d patches", ph, pw); return CGP_ERR_UNSUPPORTED; }
 
+#ifdef CGP_UMMA_TRACE
+static long long* g_umma_trace = nullptr;
+#endif
 // ---- float32 tcgen05 (UMMA) family: single-channel images, one RBF over the whole patch -------------
 static bool umma_ok(const cgp_kernel_desc* d, const Geo& g, int mode) {
   if (mode != 1 || d->C != 1 || d->dtype != CGP_F32) return false;
   const int KP = umma::pad_k(g.D);
-  return umma::smem_plan(KP, d->H * d->W, g.P).total <= 227 * 1024;
+  return umma::smem_plan(KP, d->H * d->W, g.P, g.P + 2048).total <= 227 * 1024;  // room for M <= ~2000 row sums
 }
 
 // mode: 0 Kuf fwd, 1 Kdiag fwd, 2 Kdiag bwd, 3 dW of Kuf (umma32.cuh)
@@ -271,22 +274,34 @@ static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int
   p.mode = mode;
   p.Pn = (float)g.P;
   const int p_rt = (g.P + umma::TM - 1) / umma::TM, p_ct = (g.P + umma::TN - 1) / umma::TN;
-  if (mode == 0) {
-    p.E1 = N; p.E2 = p_ct;
-    p.n_units = (long long)((M + umma::TM - 1) / umma::TM) * N * p_ct;
-  } else if (mode == 3) {
+  long long outer;
+  if (mode == 0) {  // (image, patch column tile, inducing row tile)
+    p.E1 = p_ct; p.E2 = (M + umma::TM - 1) / umma::TM;
+    outer = N;
+  } else if (mode == 3) {  // (inducing column tile, image, patch row tile)
     p.E1 = N; p.E2 = p_rt;
-    p.n_units = (long long)((M + umma::TN - 1) / umma::TN) * N * p_rt;
-  } else {
-    p.E1 = p_rt; p.E2 = p_ct;
-    p.n_units = (long long)N * p_rt * p_ct;
+    outer = (M + umma::TN - 1) / umma::TN;
+  } else {  // (image, patch column tile, patch row tile)
+    p.E1 = p_ct; p.E2 = p_rt;
+    outer = N;
   }
+  p.n_units = outer * p.E1 * p.E2;
   if (p.n_units < 1) return CGP_OK;
-  const size_t smem = umma::smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total;
-  // one persistent CTA per SM; a CTA never gets less than one whole row group, so every output
-  // element receives at most two atomic contributions (order-independent sums)
-  const long long group = mode == 3 ? 1 : p.E2;
-  const long long grid = std::max<long long>(1, std::min<long long>(p.n_units / group, num_sms()));
+#ifdef CGP_UMMA_TRACE
+  {
+    static long long* tr = nullptr;
+    if (!tr) { cudaMalloc(&tr, 64 * 24 * sizeof(long long)); }
+    cudaMemsetAsync(tr, 0, 64 * 24 * sizeof(long long), st);
+    p.trace = tr;
+    g_umma_trace = tr;
+    p.ablate = getenv("CGP_UMMA_ABLATE") ? atoi(getenv("CGP_UMMA_ABLATE")) : 0;
+  }
+#endif
+  const int racc_rows = std::max(g.P, (M + umma::TM - 1) / umma::TM * umma::TM);
+  if (racc_rows > g.P + 2048) { set_error("umma: M = %d too large", M); return CGP_ERR_UNSUPPORTED; }
+  const size_t smem = umma::smem_plan(umma::pad_k(g.D), d->H * d->W, g.P, racc_rows).total;
+  // one persistent CTA per SM walking a contiguous range of units
+  const long long grid = std::max<long long>(1, std::min<long long>(p.n_units, num_sms()));
   int dev = 0;
   CGP_CUDA_CHECK(cudaGetDevice(&dev));
 #define CALL(PH_, PW_)                                                                                        \
@@ -324,7 +339,7 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
   }
   if constexpr (std::is_same<T, float>::value) {
     static const int fam = env_choice(BWD ? "CGP_KUF_BWD_F32" : "CGP_KUF_FWD_F32", 2);  // "umma" | "mma" | "fma"
-    if (fam == 2 && !BWD && umma_ok(d, g, mode))
+    if (fam == 2 && !BWD && M <= 2048 && umma_ok(d, g, mode))
       return run_umma_rowsum(0, d, g, N, M, X, Z, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st);
   }
   static const int use_mma = env_choice(BWD ? "CGP_KUF_BWD" : "CGP_KUF_FWD", 1);
@@ -490,6 +505,31 @@ using namespace cgp;
 extern "C" {
 
 int cgp_version(void) { return CGP_VERSION; }
+
+#ifdef CGP_UMMA_TRACE
+// development only: per-unit timestamps (cycles relative to the first) of CTA 0 of the last UMMA launch
+int cgp_umma_trace_dump(void) {
+  if (!g_umma_trace) return 0;
+  long long h[64 * 24];
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, g_umma_trace, sizeof(h), cudaMemcpyDeviceToHost);
+  {
+    const long long* g = h + 63 * 24;
+    printf("CTA 0: %lld ns, %lld cycles (%.3f GHz); last CTA: %lld ns, %lld cycles; last CTA starts %lld ns after CTA 0, ends %lld ns after\n",
+           g[2] - g[0], g[3] - g[1], (double)(g[3] - g[1]) / (double)(g[2] - g[0]), g[6] - g[4], g[7] - g[5], g[4] - g[0], g[6] - g[2]);
+  }
+  long long t0 = 0;
+  for (int i = 0; i < 63 * 24; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
+  printf("unit: prod_start prod_staged iss_staged iss_tmem iss_done epi_arrive epi_mma epi_end | staged by producer warp 0..7 | epilogue end by quarter | epilogue start by quarter\n");
+  for (int u = 0; u < 63; ++u) {
+    if (!h[u * 24 + 1]) break;
+    printf("%2d:", u);
+    for (int s = 0; s < 24; ++s) printf("%s%6lld", (s == 8 || s == 16 || s == 20) ? " |" : " ", h[u * 24 + s] ? h[u * 24 + s] - t0 : -1);
+    printf("\n");
+  }
+  return 0;
+}
+#endif
 
 const char* cgp_last_error(void) { return g_err; }
 
