@@ -323,6 +323,25 @@ __device__ __forceinline__ void put_row_tmem(uint32_t taddr, const float (&hi)[K
   }
 }
 
+// Operand row from D raw values already in registers (prefetched one unit ahead).
+template <int D, int KP>
+__device__ __forceinline__ void row_from_raw(float (&x)[KP], const float (&raw)[D], bool valid, bool scaled, float s2,
+                                             float c2) {
+#pragma unroll
+  for (int d = 0; d < KP; ++d) x[d] = 0.f;
+  if (valid) {
+    float ss = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      ss = fmaf(raw[d], raw[d], ss);
+      x[d] = scaled ? raw[d] * s2 : raw[d];
+    }
+    const float en = -c2 * ss;
+    x[D] = scaled ? en : 1.f;
+    x[D + 1] = scaled ? 1.f : en;
+  }
+}
+
 // B operand row -> shared memory (UMMA no-swizzle K-major layout, hi and lo halves)
 template <int KP>
 __device__ __forceinline__ void store_row_smem(unsigned char* buf, int R, int r, const float (&x)[KP]) {
@@ -374,7 +393,7 @@ constexpr int kIssuerWarp = kProd / 32, kEpiWarp0 = kProd / 32 + 1;
 
 // shared-memory plan (bytes), shared by host and device
 struct Smem {
-  int sB, wc, img, w, racc, red, bars, total;
+  int sB, wc, img, zbuf, w, racc, red, bars, total;
 };
 __host__ __device__ inline Smem smem_plan(int KP, int HW, int P, int R) {  // R: longest row-accumulator array
   Smem s;
@@ -385,6 +404,8 @@ __host__ __device__ inline Smem smem_plan(int KP, int HW, int P, int R) {  // R:
   o += 4 * TN * 4;
   s.img = o;  // 2 raw buffers (cp.async targets) + xh, xl, sh, sl, sq; then eh, el (P each)
   o += 7 * ((HW * 4 + 15) / 16 * 16) + 2 * ((P * 4 + 15) / 16 * 16);
+  s.zbuf = o;  // two raw Z tiles (mode 0)
+  o += 2 * TM * (KP - 2) * 4;
   s.w = o;
   o += (P * 4 + 15) / 16 * 16;
   s.racc = o;  // row accumulators: [2 column halves][2 (sum k, sum k S)][P]
@@ -428,6 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
   float* sq = img0 + 6 * img_stride;              // squares (scratch of the norm pass)
   float* eh = img0 + 7 * img_stride;              // e[p] = -c2 |x_p|^2, split
   float* el = eh + (p.P * 4 + 15) / 16 * 4;
+  float* zbuf = reinterpret_cast<float*>(smem + L.zbuf);
   float* w = reinterpret_cast<float*>(smem + L.w);
   float* racc = reinterpret_cast<float*>(smem + L.racc);
   const int Pp = (Racc * 4 + 15) / 16 * 4;  // padded accumulator length (floats)
@@ -488,6 +510,15 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
     };
     UnitIter it;
     it.init(lo, p.E1, p.E2);
+    // Z rows (mode 0: a new A tile every unit) are fetched one unit ahead with cp.async: no global-memory
+    // latency and no extra registers in a producer warp's per-unit critical path
+    auto fetch_zrow = [&](int g, int buf) {
+      const float* zr = p.Z + (size_t)min(g, p.M - 1) * D;
+      float* dst = zbuf + (buf * TM + pt) * D;
+#pragma unroll
+      for (int d = 0; d < D; ++d) cp_async4(dst + d, zr + d);
+    };
+    if (a_is_z && pt < TM && nun > 0) fetch_zrow(decode(mode, it).arow + pt, 0);
     for (int u = 0; u < nun; ++u, it.next()) {
       const Unit un = decode(mode, it);
       if (pt == 0) CGP_TRACE(0, u);
@@ -532,18 +563,26 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
         }
       }
       // The A row (registers) and the column weights are prepared BEFORE waiting for the operand
-      // slots: only the TMEM / shared-memory stores sit in the MMA(u-2) -> stage -> MMA(u) loop.
+      // slots: only the TMEM / shared-memory stores sit in the MMA(u-2) -> stage -> MMA(u) loop.  Rows of
+      // Z come from global memory: their loads were issued one unit ahead (zraw), so a producer warp's
+      // per-unit critical path holds no global-memory latency.
       float ahi[KP], alo[KP];
       if (needA && pt < TM) {  // warps 0-3: row pt -> TMEM lane pt
         const int g = un.arow + pt;
         if (a_is_z) {
+          cp_async_wait_all();  // this thread's own row, fetched one unit ago
           float x[KP];
-          gather_row<PH, PW, KP>(x, g < p.M, true, 2.f * c2, c2, p.Z + (size_t)min(g, p.M - 1) * D, PW);
+          gather_row<PH, PW, KP>(x, g < p.M, true, 2.f * c2, c2, zbuf + ((u & 1) * TM + pt) * D, PW);
           split_row<KP>(x, ahi, alo);
         } else {
           const int gg = min(g, p.P - 1), o = (gg / p.Wout) * p.Wd + (gg % p.Wout);
           load_patch_row<PH, PW, KP>(ahi, alo, g < p.P, true, sh + o, sl + o, p.Wd, eh[gg], el[gg]);
         }
+      }
+      if (a_is_z && pt < TM && u + 1 < nun) {  // fetch the next unit's Z row (asynchronous, into shared memory)
+        UnitIter nx = it;
+        nx.next();
+        fetch_zrow(decode(mode, nx).arow + pt, (u + 1) & 1);
       }
       // column weights of this unit (four buffers: the epilogue of unit u-4 is certainly over)
       if (pt >= kProd - TN) {
@@ -556,9 +595,10 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
         }
         wc[(u & 3) * TN + c] = v;
       }
-      if (pt == 0) CGP_TRACE(15, u);
+      if (pt == 32) CGP_TRACE(9, u);
       if (u >= 2) mbar_wait(&mma_done[u & 1], ((u >> 1) - 1) & 1);  // the MMAs of unit u-2 have read their operands
-      if (pt == 0 && u >= 2) CGP_TRACE(23, u - 2);
+      if (pt == 32) CGP_TRACE(10, u);
+      if (pt == 0) CGP_TRACE(13, u);
       if (needA) {
         aslot ^= 1;
         akey = un.akey;
@@ -572,6 +612,8 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
           tc_fence_before();
         }
       }
+      if (pt == 32) CGP_TRACE(11, u);
+      if (pt == 0) CGP_TRACE(14, u);
       if (needB) {  // warps 2-7
         bslot ^= 1;
         bkey = un.bkey;
@@ -591,11 +633,11 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
           put_row_smem<KP>(buf, TN, r, xhi, xlo);
         }
       }
-      proxy_fence();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      if (needB) proxy_fence();  // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&staged[u & 1]);
       if (pt == 0) CGP_TRACE(1, u);
-      if (lane == 0) CGP_TRACE(8 + warp, u);
+      if (pt == 32) CGP_TRACE(15, u);
     }
     cp_async_wait_all();
   } else if (warp == kIssuerWarp) {
