@@ -323,6 +323,46 @@ static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int
 #undef CALL
 }
 
+// dZ / dvariance / dlengthscale of Kuf (umma32.cuh kuf_dz_kernel): one row tile of 128 inducing
+// patches per CTA group, the (image, patch tile) units of the tile split evenly over the group.
+static int run_umma_dz(const cgp_kernel_desc* d, const Geo& g, int N, int M, const void* X, const void* Z,
+                       const void* W, const void* var, const void* ls, const void* G, void* dZ, void* dvar,
+                       void* dls, cudaStream_t st) {
+  umma::Params p;
+  memset(&p, 0, sizeof(p));
+  p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
+  p.ls = (const float*)ls; p.G = (const float*)G; p.dZ = (float*)dZ; p.dvar = (float*)dvar; p.dls = (float*)dls;
+  p.N = N; p.M = M; p.H = d->H; p.Wd = d->W; p.Hout = g.Hout; p.Wout = g.Wout; p.P = g.P; p.D = g.D;
+  p.Pn = (float)g.P;
+  const int n_mt = (M + umma::TM - 1) / umma::TM, n_pt = (g.P + umma::TN - 1) / umma::TN;
+  const long long units = (long long)N * n_pt;
+  int per_tile = std::max(1, num_sms() / n_mt);
+  per_tile = (int)std::min<long long>(per_tile, units);
+  p.E1 = per_tile; p.E2 = n_pt;
+  const size_t smem = umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total;
+  if (smem > 227 * 1024) { set_error("umma dz: needs %zu bytes of shared memory", smem); return CGP_ERR_UNSUPPORTED; }
+  const unsigned grid = (unsigned)(n_mt * per_tile);
+  int dev = 0;
+  CGP_CUDA_CHECK(cudaGetDevice(&dev));
+#define CALL(PH_, PW_)                                                                                        \
+  {                                                                                                           \
+    auto kernel = umma::kuf_dz_kernel<PH_, PW_>;                                                              \
+    {                                                                                                         \
+      std::lock_guard<std::mutex> lk(g_launch_mu);                                                            \
+      size_t& cur = g_launch_smem[std::make_pair((const void*)kernel, dev)];                                  \
+      if (smem > cur) {                                                                                       \
+        CGP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        cur = smem;                                                                                           \
+      }                                                                                                       \
+    }                                                                                                         \
+    kernel<<<grid, umma::kDzProd + 32 + umma::kEpi, smem, st>>>(p);                                           \
+    CGP_CUDA_CHECK(cudaGetLastError());                                                                       \
+    return CGP_OK;                                                                                            \
+  }
+  CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+}
+
 template <typename T, bool BWD>
 static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N, int M, const void* X,
                         const void* Z, const void* W, const void* var, const void* ls, const void* G, void* out,
@@ -339,8 +379,16 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
   }
   if constexpr (std::is_same<T, float>::value) {
     static const int fam = env_choice(BWD ? "CGP_KUF_BWD_F32" : "CGP_KUF_FWD_F32", 2);  // "umma" | "mma" | "fma"
-    if (fam == 2 && !BWD && M <= 2048 && umma_ok(d, g, mode))
-      return run_umma_rowsum(0, d, g, N, M, X, Z, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st);
+    if (fam == 2 && M <= 2048 && umma_ok(d, g, mode) &&
+        umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total <= 227 * 1024) {
+      if (!BWD) return run_umma_rowsum(0, d, g, N, M, X, Z, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st);
+      if (dZ || dvar || dls) {
+        int rc = run_umma_dz(d, g, N, M, X, Z, W, var, ls, G, dZ, dvar, dls, st);
+        if (rc != CGP_OK) return rc;
+      }
+      if (dW && W) return run_umma_rowsum(3, d, g, N, M, X, Z, W, var, ls, G, nullptr, dW, nullptr, nullptr, st);
+      return CGP_OK;
+    }
   }
   static const int use_mma = env_choice(BWD ? "CGP_KUF_BWD" : "CGP_KUF_FWD", 1);
   if constexpr (std::is_same<T, double>::value) if (use_mma) {

@@ -847,5 +847,383 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
   }
 }
 
+
+// =====================================================================================
+// Kuf backward, dZ / dvariance / dlengthscale part (dW comes from rowsum mode 3).
+//
+// Flash-attention shaped: per unit (image n, tile of 192 patches) of one tile of 128 inducing rows
+//   GEMM1  S = Z . X^T            tf32 x3, A = Z tile (TMEM, resident), B = patches (shared memory)
+//   epilogue  coef = G[m,n]/P * w_p * ex2(S)   -> two bf16 terms c1 + c2, written back over S in TMEM
+//   GEMM2  dz += coef . X         kind::f16 (bf16), A = c1 / c2 from TMEM, B = X^T as bf16 terms x1 | x2
+//          (c1.x1 + c1.x2 + c2.x1: <= 1e-5 relative, a single bf16 or tf32 coefficient is not enough
+//           because dZ = sum coef (x - z) cancels; the sums use the same rounded coefficients)
+// and at the end dZ = sigma^2 / l^2 (dz - z * sum coef).  A CTA owns one row tile for its whole life,
+// so the dz accumulator (64 TMEM columns) is read exactly once.  TMEM: S0 | S1 | dz | Z = 512 columns.
+// =====================================================================================
+constexpr int kDzProd = 224;  // 7 producer warps; warp 7 issues; warps 8-15 epilogue
+
+struct DzSmem {
+  int sB, sBt, wc, img, org, w, red, part, bars, total;
+};
+__host__ __device__ inline DzSmem dz_smem_plan(int KP, int HW, int P) {
+  DzSmem s;
+  int o = 0;
+  s.sB = o;  // 2 slots x (hi | lo) x KP x TN floats
+  o += 2 * (2 * 4 * KP * TN);
+  s.sBt = o;  // 2 slots x 64 rows (x1 | x2 of 32 dims) x TN patches, bf16
+  o += 2 * (64 * TN * 2);
+  s.wc = o;
+  o += 4 * TN * 4;
+  s.img = o;  // 2 raw buffers + xh, xl, sq; then eh, el
+  o += 5 * ((HW * 4 + 15) / 16 * 16) + 2 * ((P * 4 + 15) / 16 * 16);
+  s.org = o;
+  o += (P * 4 + 15) / 16 * 16;
+  s.w = o;
+  o += (P * 4 + 15) / 16 * 16;
+  s.red = o;
+  o += 64;
+  s.part = o;
+  o += 2 * TM * 4;
+  s.bars = o;
+  o += 128;
+  s.total = o;
+  return s;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float odd_k, float even_k) {  // even k in the low half
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd_k), "f"(even_k));
+  return r;
+}
+
+template <int PH, int PW>
+__global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Params p) {
+  constexpr int D = PH * PW;
+  constexpr int KP = pad_k(D);
+  constexpr int KS = KP / 8;
+  static_assert(KP <= 32 && 2 * TN + 64 + 2 * KP <= 512, "TMEM budget");
+  constexpr uint32_t B_HALF = 4 * KP * TN, BT_SLOT = 64 * TN * 2;
+  constexpr uint32_t kTmemD2 = 2 * TN, kTmemA = 2 * TN + 64;
+  constexpr int kNT = kDzProd + 32 + kEpi;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int HW = p.H * p.Wd;
+  const DzSmem L = dz_smem_plan(KP, HW, p.P);
+  unsigned char* sB = smem + L.sB;
+  unsigned char* sBt = smem + L.sBt;
+  float* wc = reinterpret_cast<float*>(smem + L.wc);
+  float* img0 = reinterpret_cast<float*>(smem + L.img);
+  const int img_stride = (HW * 4 + 15) / 16 * 4;
+  float* xh = img0 + 2 * img_stride;
+  float* xl = img0 + 3 * img_stride;
+  float* sq = img0 + 4 * img_stride;
+  float* eh = img0 + 5 * img_stride;
+  float* el = eh + (p.P * 4 + 15) / 16 * 4;
+  int* org = reinterpret_cast<int*>(smem + L.org);
+  float* w = reinterpret_cast<float*>(smem + L.w);
+  float* red = reinterpret_cast<float*>(smem + L.red);
+  float* part = reinterpret_cast<float*>(smem + L.part);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* staged = bars;          // [2] producers -> issuer: B / Bt of the unit are in shared memory
+  uint64_t* g1_done = bars + 2;     // [2] GEMM1 of the unit complete (S readable)
+  uint64_t* coef_ready = bars + 4;  // [2] epilogue wrote the coefficients of the unit
+  uint64_t* g2_done = bars + 6;     // [2] GEMM2 of the unit complete (operand slot and S buffer reusable)
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // work split: blockIdx -> (row tile, share of the (image, patch tile) units of that tile)
+  const int n_pt = p.E2, per_tile = p.E1;  // E2: patch tiles per image; E1: CTAs per row tile
+  const int mtile = blockIdx.x / per_tile, share = blockIdx.x % per_tile;
+  const long long tot = (long long)p.N * n_pt;
+  const long long lo = tot * share / per_tile, hi = tot * (share + 1) / per_tile;
+  const int nun = (int)(hi - lo);
+  const int m0 = mtile * TM;
+
+  for (int i = tid; i < p.P; i += kNT) {
+    w[i] = p.Wt ? p.Wt[i] : 1.f;
+    org[i] = (i / p.Wout) * p.Wd + (i % p.Wout);
+  }
+  // the transposed bf16 operand keeps zero rows for the padded dims d >= D: clear it once
+  for (int i = tid; i < (int)(2 * BT_SLOT / 4); i += kNT) reinterpret_cast<uint32_t*>(sBt)[i] = 0u;
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&staged[b], kDzProd / 32);
+      mbar_init(&g1_done[b], 1);
+      mbar_init(&coef_ready[b], kEpi / 32);
+      mbar_init(&g2_done[b], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+  const float lsv = p.ls[0], sig2 = p.var[0];
+  const float c2 = 1.4426950408889634f / (2.f * lsv * lsv);
+
+  // A operand: the Z tile, staged once (warps 0-3, one row per thread), visible to the issuer through
+  // the first `staged` arrival
+  if (warp < 4) {
+    const int g = m0 + tid;
+    float x[KP], ahi[KP], alo[KP];
+    gather_row<PH, PW, KP>(x, g < p.M, true, 2.f * c2, c2, p.Z + (size_t)min(g, p.M - 1) * D, PW);
+    split_row<KP>(x, ahi, alo);
+    put_row_tmem<KP>(tmem_base + ((uint32_t)(tid & ~31) << 16) + kTmemA, ahi, alo);
+    tmem_wait_st();
+    tc_fence_before();
+  }
+
+  if (warp < kDzProd / 32) {
+    // ============================== producers
+    const int pt = tid;
+    int cur_img = -1, pre_img = -1, ibuf = 0;
+    auto fetch_image = [&](int n, int buf) {
+      const float* src = p.X + (size_t)n * HW;
+      float* dst = img0 + buf * img_stride;
+      for (int i = pt; i < HW; i += kDzProd) cp_async4(dst + i, src + i);
+    };
+    for (int u = 0; u < nun; ++u) {
+      const long long v = lo + u;
+      const int n = (int)(v / n_pt), j = (int)(v % n_pt);
+      if (n != cur_img) {
+        if (pre_img != n) {
+          cp_async_wait_all();
+          named_sync(1, kDzProd);
+          ibuf ^= 1;
+          fetch_image(n, ibuf);
+        } else {
+          ibuf ^= 1;
+        }
+        cp_async_wait_all();
+        named_sync(1, kDzProd);
+        cur_img = n;
+        const float* raw = img0 + ibuf * img_stride;
+        for (int i = pt; i < HW; i += kDzProd) {
+          const float x = raw[i];
+          split_tf32(x, xh[i], xl[i]);
+          sq[i] = x * x;
+        }
+        named_sync(1, kDzProd);
+        for (int q = pt; q < p.P; q += kDzProd) {
+          const float* base = sq + org[q];
+          float ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < PH; ++i)
+#pragma unroll
+            for (int jj = 0; jj < PW; ++jj) ss += base[i * p.Wd + jj];
+          split_tf32(-c2 * ss, eh[q], el[q]);
+        }
+        named_sync(1, kDzProd);
+        if (n + 1 < p.N) {
+          fetch_image(n + 1, ibuf ^ 1);
+          pre_img = n + 1;
+        }
+      }
+      const int brow = j * TN;
+      // B row of GEMM1 into registers before waiting for the slot
+      const int r = pt - (kDzProd - TN);
+      float bhi[KP], blo[KP];
+      if (r >= 0) {
+        const int g = brow + r, gg = min(g, p.P - 1), o = org[gg];
+        load_patch_row<PH, PW, KP>(bhi, blo, g < p.P, false, xh + o, xl + o, p.Wd, eh[gg], el[gg]);
+      }
+      if (pt < TN) {
+        const int col = brow + pt;
+        wc[(u & 3) * TN + pt] = col < p.P ? w[col] : 0.f;
+      }
+      if (u >= 2) mbar_wait(&g2_done[u & 1], ((u >> 1) - 1) & 1);  // both GEMMs of unit u-2 have read the slot
+      if (r >= 0) put_row_smem<KP>(sB + (u & 1) * 2 * B_HALF, TN, r, bhi, blo);
+      // transposed bf16 operand of GEMM2: item = (octet of 8 consecutive patches, dim d) -> one 16-byte
+      // chunk of row d (x1) and of row 32 + d (x2); raw pixels re-read from the image
+      {
+        const float* raw = img0 + ibuf * img_stride;
+        unsigned char* bt = sBt + (u & 1) * BT_SLOT;
+        for (int item = pt; item < (TN / 8) * D; item += kDzProd) {
+          const int oct = item % (TN / 8), d = item / (TN / 8);
+          const int doff = (d / PW) * p.Wd + (d % PW);
+          uint32_t q1[4], q2[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float xv[2], x1[2];
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int g = brow + oct * 8 + 2 * h + e2;
+              xv[e2] = g < p.P ? raw[org[g] + doff] : 0.f;
+            }
+            q1[h] = pack_bf16x2(xv[1], xv[0]);
+            x1[0] = __uint_as_float(q1[h] << 16);
+            x1[1] = __uint_as_float(q1[h] & 0xFFFF0000u);
+            q2[h] = pack_bf16x2(xv[1] - x1[1], xv[0] - x1[0]);
+          }
+          const int off = oct * (16 * 64) + (d >> 3) * 128 + (d & 7) * 16;
+          *reinterpret_cast<uint4*>(bt + off) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+          *reinterpret_cast<uint4*>(bt + off + 4 * 128) = make_uint4(q2[0], q2[1], q2[2], q2[3]);  // row 32 + d
+        }
+      }
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&staged[u & 1]);
+    }
+    cp_async_wait_all();
+  } else if (warp == kDzProd / 32) {
+    // ============================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t id1 = make_idesc(TM, TN, kFmtTF32);
+      constexpr uint32_t id2a = make_idesc(TM, 64, kFmtBF16), id2b = make_idesc(TM, 32, kFmtBF16);
+      const uint64_t dbh0 = make_desc(smem_u32(sB), 16 * TN, 128);
+      const uint64_t dbt0 = make_desc(smem_u32(sBt), 16 * 64, 128);
+      const uint32_t ah = tmem_base + kTmemA, al = ah + KP, d2 = tmem_base + kTmemD2;
+      auto gemm2 = [&](int u) {
+        mbar_wait(&coef_ready[u & 1], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sc = tmem_base + (uint32_t)(u & 1) * TN;
+        const uint64_t dbt = dbt0 + (uint64_t)((u & 1) * (BT_SLOT >> 4));
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int t = 0; t < 6; ++t) {
+            const uint64_t db = dbt + (uint64_t)(((h * 96 + t * 16) / 8) * ((16 * 64) >> 4));
+            mma_bf16_ts(d2, sc + h * 96 + 8 * t, db, id2a, (u | h | t) != 0);  // c1 . [x1 | x2]
+            mma_bf16_ts(d2, sc + h * 96 + 48 + 8 * t, db, id2b, 1);            // c2 . x1
+          }
+        mma_commit(&g2_done[u & 1]);
+      };
+      for (int u = 0; u < nun; ++u) {
+        mbar_wait(&staged[u & 1], (u >> 1) & 1);
+        tc_fence_after();
+        // the S buffer (u & 1) was last read by GEMM2(u-2), which precedes this in issue order
+        const uint64_t dbh = dbh0 + (uint64_t)((u & 1) * ((2 * B_HALF) >> 4));
+        const uint64_t dbl = dbh + (uint64_t)(B_HALF >> 4);
+        const uint32_t dcol = tmem_base + (uint32_t)(u & 1) * TN;
+#pragma unroll
+        for (int s2 = 0; s2 < KS; ++s2) {
+          const uint64_t ob = (uint64_t)((s2 * 2 * 16 * TN) >> 4);
+          mma_tf32_ts(dcol, al + 8 * s2, dbh + ob, id1, s2 > 0);
+          mma_tf32_ts(dcol, ah + 8 * s2, dbl + ob, id1, 1);
+          mma_tf32_ts(dcol, ah + 8 * s2, dbh + ob, id1, 1);
+        }
+        mma_commit(&g1_done[u & 1]);
+        if (u >= 1) gemm2(u - 1);
+      }
+      if (nun >= 1) gemm2(nun - 1);
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue
+    const int ew = warp - (kDzProd / 32 + 1);
+    const int quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const int et = tid - (kDzProd + 32);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int m = m0 + row;
+    const bool mval = m < p.M;
+    float s0 = 0.f, s2 = 0.f;  // sum coef, sum coef * S over this thread's columns
+    const float invP = 1.f / p.Pn;
+    float gnext = 0.f;
+    if (nun > 0 && mval) gnext = p.G[(size_t)m * p.N + (int)(lo / n_pt)];
+    for (int u = 0; u < nun; ++u) {
+      const float Gm = gnext * invP;
+      if (u + 1 < nun && mval) gnext = p.G[(size_t)m * p.N + (int)((lo + u + 1) / n_pt)];
+      mbar_wait(&g1_done[u & 1], (u >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbuf = lane_addr + (uint32_t)(u & 1) * TN + (uint32_t)half * 96;
+      const float4* wc4 = reinterpret_cast<const float4*>(wc + (u & 3) * TN + half * 96);
+      uint32_t c2hold[48];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tbuf + 32 * c, v);
+        tmem_wait_ld(v);
+        uint32_t c1p[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 wq = wc4[8 * c + q];
+          const float ww[4] = {wq.x, wq.y, wq.z, wq.w};
+          float cf[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float s = __uint_as_float(v[4 * q + i]);
+            cf[i] = Gm * ww[i] * ex2f(s);
+            s2 = fmaf(cf[i], s, s2);
+          }
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const uint32_t a1 = pack_bf16x2(cf[2 * h2 + 1], cf[2 * h2]);
+            const float f0 = __uint_as_float(a1 << 16), f1 = __uint_as_float(a1 & 0xFFFF0000u);
+            const uint32_t a2 = pack_bf16x2(cf[2 * h2 + 1] - f1, cf[2 * h2] - f0);
+            s0 += (f0 + __uint_as_float(a2 << 16)) + (f1 + __uint_as_float(a2 & 0xFFFF0000u));
+            c1p[2 * q + h2] = a1;
+            c2hold[16 * c + 2 * q + h2] = a2;
+          }
+        }
+        // c1 of this chunk goes to packed columns 16 c .. 16 c + 15 of the half: already consumed
+        tmem_st8(tbuf + 16 * c, c1p);
+        tmem_st8(tbuf + 16 * c + 8, c1p + 8);
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tmem_st8(tbuf + 48 + 8 * k, c2hold + 8 * k);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&coef_ready[u & 1]);
+    }
+    // ---- the row tile is complete: dZ, dvariance, dlengthscale
+    if (nun > 0) {
+      mbar_wait(&g2_done[(nun - 1) & 1], ((nun - 1) >> 1) & 1);
+      tc_fence_after();
+    }
+    if (half == 1) {
+      part[row] = s0;
+    }
+    named_sync(2, kEpi);
+    const float s0row = half == 0 ? s0 + part[row] : 0.f;
+    if (half == 0 && nun > 0 && p.dZ) {  // warp-uniform: tcgen05.ld is a warp-collective
+      uint32_t d1[32], dd2[32];
+      tmem_ld32(lane_addr + kTmemD2, d1);
+      tmem_ld32(lane_addr + kTmemD2 + 32, dd2);
+      tmem_wait_ld(d1);
+      tmem_wait_ld(dd2);
+      if (mval) {
+        const float sc = sig2 / (lsv * lsv);
+        const float* zr = p.Z + (size_t)m * D;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float dz = __uint_as_float(d1[d]) + __uint_as_float(dd2[d]);
+          atomicAdd(p.dZ + (size_t)m * D + d, sc * (dz - zr[d] * s0row));
+        }
+      }
+    }
+    {
+      float t0 = warp_sum(mval ? s0 : 0.f), t2 = warp_sum(mval ? s2 : 0.f);
+      named_sync(2, kEpi);
+      if (lane == 0) {
+        red[ew] = t0;
+        red[8 + ew] = t2;
+      }
+      named_sync(2, kEpi);
+      if (et == 0) {
+        float a0 = 0.f, a2 = 0.f;
+        for (int k = 0; k < 8; ++k) {
+          a0 += red[k];
+          a2 += red[8 + k];
+        }
+        if (p.dvar) atomicAdd(p.dvar, a0);
+        if (p.dls) atomicAdd(p.dls, -2.f * sig2 / lsv * a2 / 1.4426950408889634f);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 }  // namespace umma
 }  // namespace cgp
