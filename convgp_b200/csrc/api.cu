@@ -339,6 +339,15 @@ static int run_umma_dz(const cgp_kernel_desc* d, const Geo& g, int N, int M, con
   int per_tile = std::max(1, num_sms() / n_mt);
   per_tile = (int)std::min<long long>(per_tile, units);
   p.E1 = per_tile; p.E2 = n_pt;
+#ifdef CGP_UMMA_TRACE
+  {
+    static long long* tr = nullptr;
+    if (!tr) { cudaMalloc(&tr, 64 * 24 * sizeof(long long)); }
+    cudaMemsetAsync(tr, 0, 64 * 24 * sizeof(long long), st);
+    p.trace = tr;
+    g_umma_trace = tr;
+  }
+#endif
   const size_t smem = umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total;
   if (smem > 227 * 1024) { set_error("umma dz: needs %zu bytes of shared memory", smem); return CGP_ERR_UNSUPPORTED; }
   const unsigned grid = (unsigned)(n_mt * per_tile);
@@ -382,12 +391,15 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     if (fam == 2 && M <= 2048 && umma_ok(d, g, mode) &&
         umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total <= 227 * 1024) {
       if (!BWD) return run_umma_rowsum(0, d, g, N, M, X, Z, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st);
+      // the backward kernel's two-deep ring of per-image arrays needs at least two patch tiles per image
+      if (g.P > umma::TN) {
       if (dZ || dvar || dls) {
         int rc = run_umma_dz(d, g, N, M, X, Z, W, var, ls, G, dZ, dvar, dls, st);
         if (rc != CGP_OK) return rc;
       }
       if (dW && W) return run_umma_rowsum(3, d, g, N, M, X, Z, W, var, ls, G, nullptr, dW, nullptr, nullptr, st);
       return CGP_OK;
+      }
     }
   }
   static const int use_mma = env_choice(BWD ? "CGP_KUF_BWD" : "CGP_KUF_FWD", 1);
@@ -563,7 +575,7 @@ int cgp_umma_trace_dump(void) {
   cudaMemcpy(h, g_umma_trace, sizeof(h), cudaMemcpyDeviceToHost);
   {
     const long long* g = h + 63 * 24;
-    printf("CTA 0: %lld ns, %lld cycles (%.3f GHz); last CTA: %lld ns, %lld cycles; last CTA starts %lld ns after CTA 0, ends %lld ns after\n",
+    if (g[2]) printf("CTA 0: %lld ns, %lld cycles (%.3f GHz); last CTA: %lld ns, %lld cycles; last CTA starts %lld ns after CTA 0, ends %lld ns after\n",
            g[2] - g[0], g[3] - g[1], (double)(g[3] - g[1]) / (double)(g[2] - g[0]), g[6] - g[4], g[7] - g[5], g[4] - g[0], g[6] - g[2]);
   }
   long long t0 = 0;

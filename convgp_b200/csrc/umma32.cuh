@@ -860,22 +860,27 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
 // and at the end dZ = sigma^2 / l^2 (dz - z * sum coef).  A CTA owns one row tile for its whole life,
 // so the dz accumulator (64 TMEM columns) is read exactly once.  TMEM: S0 | S1 | dz | Z = 512 columns.
 // =====================================================================================
-constexpr int kDzProd = 224;  // 7 producer warps; warp 7 issues; warps 8-15 epilogue
+constexpr int kDzProd = 224;  // warps 0-7 epilogue, 8-14 producers (7 warps), 15 issues the MMAs
 
 struct DzSmem {
-  int sB, sBt, wc, img, org, w, red, part, bars, total;
+  int sB, sBt, wc, img, pre, pre_stride, org, w, red, part, bars, total;
 };
 __host__ __device__ inline DzSmem dz_smem_plan(int KP, int HW, int P) {
   DzSmem s;
   int o = 0;
   s.sB = o;  // 2 slots x (hi | lo) x KP x TN floats
   o += 2 * (2 * 4 * KP * TN);
-  s.sBt = o;  // 2 slots x 64 rows (x1 | x2 of 32 dims) x TN patches, bf16
-  o += 2 * (64 * TN * 2);
+  s.sBt = o;  // 3 slots x 64 rows (x1 | x2 of 32 dims) x TN patches, bf16
+  o += 3 * (64 * TN * 2);
   s.wc = o;
   o += 4 * TN * 4;
-  s.img = o;  // 2 raw buffers + xh, xl, sq; then eh, el
-  o += 5 * ((HW * 4 + 15) / 16 * 16) + 2 * ((P * 4 + 15) / 16 * 16);
+  s.img = o;  // 3 raw image buffers (cp.async ring)
+  o += 3 * ((HW * 4 + 15) / 16 * 16);
+  // per-image derived arrays, two-deep ring: xh, xl (tf32 split pixels), four packed-bf16 pair arrays
+  // (x1 / x2 terms, pairs starting at even / odd pixels), eh, el (split patch norms)
+  s.pre = o;
+  s.pre_stride = 2 * ((HW * 4 + 15) / 16 * 16) + 4 * (((HW / 2 + 2) * 4 + 15) / 16 * 16) + 2 * ((P * 4 + 15) / 16 * 16);
+  o += 2 * s.pre_stride;
   s.org = o;
   o += (P * 4 + 15) / 16 * 16;
   s.w = o;
@@ -885,7 +890,7 @@ __host__ __device__ inline DzSmem dz_smem_plan(int KP, int HW, int P) {
   s.part = o;
   o += 2 * TM * 4;
   s.bars = o;
-  o += 128;
+  o += 160;
   s.total = o;
   return s;
 }
@@ -913,21 +918,19 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
   float* wc = reinterpret_cast<float*>(smem + L.wc);
   float* img0 = reinterpret_cast<float*>(smem + L.img);
   const int img_stride = (HW * 4 + 15) / 16 * 4;
-  float* xh = img0 + 2 * img_stride;
-  float* xl = img0 + 3 * img_stride;
-  float* sq = img0 + 4 * img_stride;
-  float* eh = img0 + 5 * img_stride;
-  float* el = eh + (p.P * 4 + 15) / 16 * 4;
   int* org = reinterpret_cast<int*>(smem + L.org);
   float* w = reinterpret_cast<float*>(smem + L.w);
   float* red = reinterpret_cast<float*>(smem + L.red);
   float* part = reinterpret_cast<float*>(smem + L.part);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-  uint64_t* staged = bars;          // [2] producers -> issuer: B / Bt of the unit are in shared memory
-  uint64_t* g1_done = bars + 2;     // [2] GEMM1 of the unit complete (S readable)
+  uint64_t* staged = bars;          // [2] producers -> issuer: GEMM1's B operand of the unit is in shared memory
+  uint64_t* g1_done = bars + 2;     // [2] GEMM1 of the unit complete (S readable, its B slot reusable)
   uint64_t* coef_ready = bars + 4;  // [2] epilogue wrote the coefficients of the unit
-  uint64_t* g2_done = bars + 6;     // [2] GEMM2 of the unit complete (operand slot and S buffer reusable)
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* g2_done = bars + 6;     // [3] GEMM2 of the unit complete (its transposed-operand slot reusable)
+  uint64_t* staged_t = bars + 9;    // [3] producers -> issuer: GEMM2's B operand of the unit is in shared memory
+  uint64_t* img_bar = bars + 12;    // [3] image ring: all cp.async of a buffer have landed
+  uint64_t* pre_bar = bars + 15;    // [2] derived arrays of an image are complete
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // work split: blockIdx -> (row tile, share of the (image, patch tile) units of that tile)
@@ -943,14 +946,19 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
     org[i] = (i / p.Wout) * p.Wd + (i % p.Wout);
   }
   // the transposed bf16 operand keeps zero rows for the padded dims d >= D: clear it once
-  for (int i = tid; i < (int)(2 * BT_SLOT / 4); i += kNT) reinterpret_cast<uint32_t*>(sBt)[i] = 0u;
+  for (int i = tid; i < (int)(3 * BT_SLOT / 4); i += kNT) reinterpret_cast<uint32_t*>(sBt)[i] = 0u;
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&staged[b], kDzProd / 32);
       mbar_init(&g1_done[b], 1);
       mbar_init(&coef_ready[b], kEpi / 32);
-      mbar_init(&g2_done[b], 1);
     }
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(&g2_done[b], 1);
+      mbar_init(&staged_t[b], kDzProd / 32);
+      mbar_init(&img_bar[b], kDzProd);
+    }
+    for (int b = 0; b < 2; ++b) mbar_init(&pre_bar[b], kDzProd);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -968,64 +976,90 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
 
   // A operand: the Z tile, staged once (warps 0-3, one row per thread), visible to the issuer through
   // the first `staged` arrival
-  if (warp < 4) {
-    const int g = m0 + tid;
+  if (warp >= 8 && warp < 12) {
+    const int rowA = tid - kEpi, g = m0 + rowA;
     float x[KP], ahi[KP], alo[KP];
     gather_row<PH, PW, KP>(x, g < p.M, true, 2.f * c2, c2, p.Z + (size_t)min(g, p.M - 1) * D, PW);
     split_row<KP>(x, ahi, alo);
-    put_row_tmem<KP>(tmem_base + ((uint32_t)(tid & ~31) << 16) + kTmemA, ahi, alo);
+    put_row_tmem<KP>(tmem_base + ((uint32_t)(rowA & ~31) << 16) + kTmemA, ahi, alo);
     tmem_wait_st();
     tc_fence_before();
   }
 
-  if (warp < kDzProd / 32) {
+  // Warp order = scheduling priority (higher warp ids win the issue slot): the MMA issuer has few but
+  // latency-critical instructions (warp 15), the producers feed it (warps 8-14), and the eight
+  // instruction-heavy epilogue warps take what is left (warps 0-7).
+  if (warp >= kEpi / 32 && warp < kEpi / 32 + kDzProd / 32) {
     // ============================== producers
-    const int pt = tid;
-    int cur_img = -1, pre_img = -1, ibuf = 0;
-    auto fetch_image = [&](int n, int buf) {
+    const int pt = tid - kEpi;
+    // Images stream through a three-deep cp.async ring; each buffer has an mbarrier that completes when
+    // every producer thread's copies have landed, so no producer ever waits for another at a CTA barrier
+    // (producer warps run up to two units apart).  Image k of this CTA lives in buffer k % 3.
+    int cur_img = -1, ki = -1;
+    auto fetch_image = [&](int n, int k) {
       const float* src = p.X + (size_t)n * HW;
-      float* dst = img0 + buf * img_stride;
+      float* dst = img0 + (k % 3) * img_stride;
       for (int i = pt; i < HW; i += kDzProd) cp_async4(dst + i, src + i);
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&img_bar[k % 3])) : "memory");
     };
+    if (nun > 0) fetch_image((int)(lo / n_pt), 0);
+    // derived arrays of the current image (ring slot ki & 1)
+    const int hw_al = (HW * 4 + 15) / 16 * 4, pk_al = ((HW / 2 + 2) * 4 + 15) / 16 * 4, p_al = (p.P * 4 + 15) / 16 * 4;
+    unsigned char* pre0 = smem + L.pre;
+    const float *xh = nullptr, *xl = nullptr, *eh = nullptr, *el = nullptr;
+    const uint32_t *pk1e = nullptr, *pk1o = nullptr, *pk2e = nullptr, *pk2o = nullptr;
     for (int u = 0; u < nun; ++u) {
       const long long v = lo + u;
       const int n = (int)(v / n_pt), j = (int)(v % n_pt);
+      if (pt == 0) CGP_TRACE(0, u);
       if (n != cur_img) {
-        if (pre_img != n) {
-          cp_async_wait_all();
-          named_sync(1, kDzProd);
-          ibuf ^= 1;
-          fetch_image(n, ibuf);
-        } else {
-          ibuf ^= 1;
-        }
-        cp_async_wait_all();
-        named_sync(1, kDzProd);
         cur_img = n;
-        const float* raw = img0 + ibuf * img_stride;
-        for (int i = pt; i < HW; i += kDzProd) {
-          const float x = raw[i];
-          split_tf32(x, xh[i], xl[i]);
-          sq[i] = x * x;
+        ++ki;
+        if (n + 1 < p.N) fetch_image(n + 1, ki + 1);  // buffer (ki + 1) % 3 held image ki - 2: nobody reads it
+        mbar_wait(&img_bar[ki % 3], (ki / 3) & 1);
+        const float* raw = img0 + (ki % 3) * img_stride;
+        float* wxh = reinterpret_cast<float*>(pre0 + (ki & 1) * L.pre_stride);
+        float* wxl = wxh + hw_al;
+        uint32_t* w1e = reinterpret_cast<uint32_t*>(wxl + hw_al);
+        uint32_t* w1o = w1e + pk_al;
+        uint32_t* w2e = w1o + pk_al;
+        uint32_t* w2o = w2e + pk_al;
+        float* weh = reinterpret_cast<float*>(w2o + pk_al);
+        float* wel = weh + p_al;
+        // every split is done once per image pixel here, not once per patch element in the unit loop
+        for (int i = pt; 2 * i < HW; i += kDzProd) {
+          float x[3], b1[3], b2[3];
+#pragma unroll
+          for (int e2 = 0; e2 < 3; ++e2) {
+            x[e2] = 2 * i + e2 < HW ? raw[2 * i + e2] : 0.f;
+            const uint32_t t1 = pack_bf16x2(0.f, x[e2]);
+            b1[e2] = __uint_as_float(t1 << 16);
+            b2[e2] = x[e2] - b1[e2];
+          }
+          split_tf32(x[0], wxh[2 * i], wxl[2 * i]);
+          if (2 * i + 1 < HW) split_tf32(x[1], wxh[2 * i + 1], wxl[2 * i + 1]);
+          w1e[i] = pack_bf16x2(b1[1], b1[0]);
+          w1o[i] = pack_bf16x2(b1[2], b1[1]);
+          w2e[i] = pack_bf16x2(b2[1], b2[0]);
+          w2o[i] = pack_bf16x2(b2[2], b2[1]);
         }
-        named_sync(1, kDzProd);
         for (int q = pt; q < p.P; q += kDzProd) {
-          const float* base = sq + org[q];
+          const float* base = raw + org[q];
           float ss = 0.f;
 #pragma unroll
           for (int i = 0; i < PH; ++i)
 #pragma unroll
-            for (int jj = 0; jj < PW; ++jj) ss += base[i * p.Wd + jj];
-          split_tf32(-c2 * ss, eh[q], el[q]);
+            for (int jj = 0; jj < PW; ++jj) ss = fmaf(base[i * p.Wd + jj], base[i * p.Wd + jj], ss);
+          split_tf32(-c2 * ss, weh[q], wel[q]);
         }
-        named_sync(1, kDzProd);
-        if (n + 1 < p.N) {
-          fetch_image(n + 1, ibuf ^ 1);
-          pre_img = n + 1;
-        }
+        mbar_arrive(&pre_bar[ki & 1]);
+        mbar_wait(&pre_bar[ki & 1], (ki >> 1) & 1);
+        xh = wxh; xl = wxl; pk1e = w1e; pk1o = w1o; pk2e = w2e; pk2o = w2o; eh = weh; el = wel;
       }
+      const float* raw = img0 + (ki % 3) * img_stride;
+      if (pt == 64) CGP_TRACE(8, u);
       const int brow = j * TN;
-      // B row of GEMM1 into registers before waiting for the slot
+      // B row of GEMM1 into registers before waiting for the slot: pure loads from the split arrays
       const int r = pt - (kDzProd - TN);
       float bhi[KP], blo[KP];
       if (r >= 0) {
@@ -1036,41 +1070,75 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
         const int col = brow + pt;
         wc[(u & 3) * TN + pt] = col < p.P ? w[col] : 0.f;
       }
-      if (u >= 2) mbar_wait(&g2_done[u & 1], ((u >> 1) - 1) & 1);  // both GEMMs of unit u-2 have read the slot
-      if (r >= 0) put_row_smem<KP>(sB + (u & 1) * 2 * B_HALF, TN, r, bhi, blo);
-      // transposed bf16 operand of GEMM2: item = (octet of 8 consecutive patches, dim d) -> one 16-byte
-      // chunk of row d (x1) and of row 32 + d (x2); raw pixels re-read from the image
+      // transposed bf16 operand of GEMM2, prepared in registers too: item = (octet of 8 consecutive
+      // patches, dim d) -> one 16-byte chunk of row d (x1) and of row 32 + d (x2)
+      constexpr int kItems = (TN / 8) * D, kPer = (kItems + kDzProd - 1) / kDzProd;
+      uint32_t q1[kPer][4], q2[kPer][4];
       {
-        const float* raw = img0 + ibuf * img_stride;
-        unsigned char* bt = sBt + (u & 1) * BT_SLOT;
-        for (int item = pt; item < (TN / 8) * D; item += kDzProd) {
-          const int oct = item % (TN / 8), d = item / (TN / 8);
-          const int doff = (d / PW) * p.Wd + (d % PW);
-          uint32_t q1[4], q2[4];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            float xv[2], x1[2];
+        for (int it2 = 0; it2 < kPer; ++it2) {
+          const int item = pt + it2 * kDzProd;
+          if (item < kItems) {
+            const int oct = item % (TN / 8), d = item / (TN / 8);
+            const int doff = (d / PW) * p.Wd + (d % PW);
+            const int g0 = brow + oct * 8;
+            if ((p.Wout & 7) == 0 && g0 + 8 <= p.P) {  // the octet lies in one patch row: 8 consecutive pixels
+              const int o = org[g0] + doff;
+              const uint32_t* s1 = (o & 1) ? pk1o + (o >> 1) : pk1e + (o >> 1);
+              const uint32_t* s2 = (o & 1) ? pk2o + (o >> 1) : pk2e + (o >> 1);
 #pragma unroll
-            for (int e2 = 0; e2 < 2; ++e2) {
-              const int g = brow + oct * 8 + 2 * h + e2;
-              xv[e2] = g < p.P ? raw[org[g] + doff] : 0.f;
+              for (int h = 0; h < 4; ++h) {
+                q1[it2][h] = s1[h];
+                q2[it2][h] = s2[h];
+              }
+            } else {
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                float xv[2];
+#pragma unroll
+                for (int e2 = 0; e2 < 2; ++e2) {
+                  const int g = g0 + 2 * h + e2;
+                  xv[e2] = g < p.P ? raw[org[g] + doff] : 0.f;
+                }
+                const uint32_t a1 = pack_bf16x2(xv[1], xv[0]);
+                q1[it2][h] = a1;
+                q2[it2][h] = pack_bf16x2(xv[1] - __uint_as_float(a1 & 0xFFFF0000u), xv[0] - __uint_as_float(a1 << 16));
+              }
             }
-            q1[h] = pack_bf16x2(xv[1], xv[0]);
-            x1[0] = __uint_as_float(q1[h] << 16);
-            x1[1] = __uint_as_float(q1[h] & 0xFFFF0000u);
-            q2[h] = pack_bf16x2(xv[1] - x1[1], xv[0] - x1[0]);
           }
-          const int off = oct * (16 * 64) + (d >> 3) * 128 + (d & 7) * 16;
-          *reinterpret_cast<uint4*>(bt + off) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
-          *reinterpret_cast<uint4*>(bt + off + 4 * 128) = make_uint4(q2[0], q2[1], q2[2], q2[3]);  // row 32 + d
+        }
+      }
+      if (pt == 64) CGP_TRACE(9, u);
+      if (u >= 2) mbar_wait(&g1_done[u & 1], ((u >> 1) - 1) & 1);  // GEMM1 of unit u-2 has read its slot
+      if (pt == 64) CGP_TRACE(10, u);
+      if (r >= 0) put_row_smem<KP>(sB + (u & 1) * 2 * B_HALF, TN, r, bhi, blo);
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&staged[u & 1]);
+      if (pt == 64) CGP_TRACE(14, u);
+      if (u >= 3) mbar_wait(&g2_done[u % 3], ((u / 3) - 1) & 1);
+      if (pt == 64) CGP_TRACE(15, u);  // GEMM2 of unit u-3 has read its slot
+      {
+        unsigned char* bt = sBt + (u % 3) * BT_SLOT;
+#pragma unroll
+        for (int it2 = 0; it2 < kPer; ++it2) {
+          const int item = pt + it2 * kDzProd;
+          if (item < kItems) {
+            const int oct = item % (TN / 8), d = item / (TN / 8);
+            const int off = oct * (16 * 64) + (d >> 3) * 128 + (d & 7) * 16;
+            *reinterpret_cast<uint4*>(bt + off) = make_uint4(q1[it2][0], q1[it2][1], q1[it2][2], q1[it2][3]);
+            *reinterpret_cast<uint4*>(bt + off + 4 * 128) = make_uint4(q2[it2][0], q2[it2][1], q2[it2][2], q2[it2][3]);
+          }
         }
       }
       proxy_fence();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&staged[u & 1]);
+      if (lane == 0) mbar_arrive(&staged_t[u % 3]);
+      if (pt == 0) CGP_TRACE(1, u);
+      if (pt == 64) CGP_TRACE(11, u);
     }
     cp_async_wait_all();
-  } else if (warp == kDzProd / 32) {
+  } else if (warp == kEpi / 32 + kDzProd / 32) {
     // ============================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t id1 = make_idesc(TM, TN, kFmtTF32);
@@ -1079,10 +1147,12 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
       const uint64_t dbt0 = make_desc(smem_u32(sBt), 16 * 64, 128);
       const uint32_t ah = tmem_base + kTmemA, al = ah + KP, d2 = tmem_base + kTmemD2;
       auto gemm2 = [&](int u) {
+        mbar_wait(&staged_t[u % 3], (u / 3) & 1);
         mbar_wait(&coef_ready[u & 1], (u >> 1) & 1);
+        CGP_TRACE(12, u);
         tc_fence_after();
         const uint32_t sc = tmem_base + (uint32_t)(u & 1) * TN;
-        const uint64_t dbt = dbt0 + (uint64_t)((u & 1) * (BT_SLOT >> 4));
+        const uint64_t dbt = dbt0 + (uint64_t)((u % 3) * (BT_SLOT >> 4));
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -1091,10 +1161,12 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
             mma_bf16_ts(d2, sc + h * 96 + 8 * t, db, id2a, (u | h | t) != 0);  // c1 . [x1 | x2]
             mma_bf16_ts(d2, sc + h * 96 + 48 + 8 * t, db, id2b, 1);            // c2 . x1
           }
-        mma_commit(&g2_done[u & 1]);
+        mma_commit(&g2_done[u % 3]);
+        CGP_TRACE(13, u);
       };
       for (int u = 0; u < nun; ++u) {
         mbar_wait(&staged[u & 1], (u >> 1) & 1);
+        CGP_TRACE(2, u);
         tc_fence_after();
         // the S buffer (u & 1) was last read by GEMM2(u-2), which precedes this in issue order
         const uint64_t dbh = dbh0 + (uint64_t)((u & 1) * ((2 * B_HALF) >> 4));
@@ -1108,6 +1180,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
           mma_tf32_ts(dcol, ah + 8 * s2, dbh + ob, id1, 1);
         }
         mma_commit(&g1_done[u & 1]);
+        CGP_TRACE(4, u);
         if (u >= 1) gemm2(u - 1);
       }
       if (nun >= 1) gemm2(nun - 1);
@@ -1115,10 +1188,10 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
     __syncwarp();
   } else {
     // ============================== epilogue
-    const int ew = warp - (kDzProd / 32 + 1);
+    const int ew = warp;
     const int quarter = warp & 3, half = ew >> 2;
     const int row = quarter * 32 + lane;
-    const int et = tid - (kDzProd + 32);
+    const int et = tid;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int m = m0 + row;
     const bool mval = m < p.M;
@@ -1129,7 +1202,9 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
     for (int u = 0; u < nun; ++u) {
       const float Gm = gnext * invP;
       if (u + 1 < nun && mval) gnext = p.G[(size_t)m * p.N + (int)((lo + u + 1) / n_pt)];
+      if (et == 0) CGP_TRACE(5, u);
       mbar_wait(&g1_done[u & 1], (u >> 1) & 1);
+      if (et == 0) CGP_TRACE(6, u);
       tc_fence_after();
       const uint32_t tbuf = lane_addr + (uint32_t)(u & 1) * TN + (uint32_t)half * 96;
       const float4* wc4 = reinterpret_cast<const float4*>(wc + (u & 3) * TN + half * 96);
@@ -1149,6 +1224,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
           for (int i = 0; i < 4; ++i) {
             const float s = __uint_as_float(v[4 * q + i]);
             cf[i] = Gm * ww[i] * ex2f(s);
+            s0 += cf[i];
             s2 = fmaf(cf[i], s, s2);
           }
 #pragma unroll
@@ -1156,7 +1232,6 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
             const uint32_t a1 = pack_bf16x2(cf[2 * h2 + 1], cf[2 * h2]);
             const float f0 = __uint_as_float(a1 << 16), f1 = __uint_as_float(a1 & 0xFFFF0000u);
             const uint32_t a2 = pack_bf16x2(cf[2 * h2 + 1] - f1, cf[2 * h2] - f0);
-            s0 += (f0 + __uint_as_float(a2 << 16)) + (f1 + __uint_as_float(a2 & 0xFFFF0000u));
             c1p[2 * q + h2] = a1;
             c2hold[16 * c + 2 * q + h2] = a2;
           }
@@ -1171,10 +1246,11 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&coef_ready[u & 1]);
+      if (et == 0) CGP_TRACE(7, u);
     }
     // ---- the row tile is complete: dZ, dvariance, dlengthscale
     if (nun > 0) {
-      mbar_wait(&g2_done[(nun - 1) & 1], ((nun - 1) >> 1) & 1);
+      mbar_wait(&g2_done[(nun - 1) % 3], ((nun - 1) / 3) & 1);
       tc_fence_after();
     }
     if (half == 1) {

@@ -19,6 +19,7 @@ fns = {
     "kuf_fwd": lambda: L.cgp_kuf_fwd(s.ref(), hp.N, hp.M, p(hp.X), p(hp.Z), p(hp.W), p(hp.variance), p(hp.lengthscales), p(hp.Kuf), None, 0, st()),
     "kdiag_fwd": lambda: L.cgp_kdiag_fwd(s.ref(), hp.N, p(hp.X), p(hp.W), p(hp.variance), p(hp.lengthscales), p(hp.Kdiag), None, 0, st()),
     "kuf_bwd": lambda: L.cgp_kuf_bwd(s.ref(), hp.N, hp.M, p(hp.X), p(hp.Z), p(hp.W), p(hp.variance), p(hp.lengthscales), p(hp.G), p(hp.dZ), p(hp.dW), p(hp.dvar), p(hp.dls), None, 0, st()),
+    "kuf_bwd_dz": lambda: L.cgp_kuf_bwd(s.ref(), hp.N, hp.M, p(hp.X), p(hp.Z), p(hp.W), p(hp.variance), p(hp.lengthscales), p(hp.G), p(hp.dZ), None, p(hp.dvar), p(hp.dls), None, 0, st()),
     "kdiag_bwd": lambda: L.cgp_kdiag_bwd(s.ref(), hp.N, p(hp.X), p(hp.W), p(hp.variance), p(hp.lengthscales), p(hp.gd), p(hp.dW), p(hp.dvar), p(hp.dls), None, 0, st()),
 }
 for i in range(3):
