@@ -255,10 +255,11 @@ static int launch_fast(K kernel, P& p, int tpb, size_t smem, cudaStream_t st, co
 static long long* g_umma_trace = nullptr;
 #endif
 // ---- float32 tcgen05 (UMMA) family: single-channel images, one RBF over the whole patch -------------
-static bool umma_ok(const cgp_kernel_desc* d, const Geo& g, int mode) {
+static bool umma_ok(const cgp_kernel_desc* d, const Geo& g, int mode, int M) {
   if (mode != 1 || d->C != 1 || d->dtype != CGP_F32) return false;
   const int KP = umma::pad_k(g.D);
-  return umma::smem_plan(KP, d->H * d->W, g.P, g.P + 2048).total <= 227 * 1024;  // room for M <= ~2000 row sums
+  const int racc_rows = std::max(g.P, (M + umma::TM - 1) / umma::TM * umma::TM);
+  return umma::smem_plan(KP, d->H * d->W, g.P, racc_rows).total <= 227 * 1024;
 }
 
 // mode: 0 Kuf fwd, 1 Kdiag fwd, 2 Kdiag bwd, 3 dW of Kuf (umma32.cuh)
@@ -298,7 +299,6 @@ static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int
   }
 #endif
   const int racc_rows = std::max(g.P, (M + umma::TM - 1) / umma::TM * umma::TM);
-  if (racc_rows > g.P + 2048) { set_error("umma: M = %d too large", M); return CGP_ERR_UNSUPPORTED; }
   const size_t smem = umma::smem_plan(umma::pad_k(g.D), d->H * d->W, g.P, racc_rows).total;
   // one persistent CTA per SM walking a contiguous range of units
   const long long grid = std::max<long long>(1, std::min<long long>(p.n_units, num_sms()));
@@ -388,7 +388,7 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
   }
   if constexpr (std::is_same<T, float>::value) {
     static const int fam = env_choice(BWD ? "CGP_KUF_BWD_F32" : "CGP_KUF_FWD_F32", 2);  // "umma" | "mma" | "fma"
-    if (fam == 2 && M <= 2048 && umma_ok(d, g, mode) &&
+    if (fam == 2 && umma_ok(d, g, mode, M) &&
         umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total <= 227 * 1024) {
       if (!BWD) return run_umma_rowsum(0, d, g, N, M, X, Z, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st);
       // the backward kernel's two-deep ring of per-image arrays needs at least two patch tiles per image
@@ -473,7 +473,7 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
     CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
   }
   if constexpr (std::is_same<T, float>::value) {
-    if (use_tc32 == 2 && umma_ok(d, g, mode))
+    if (use_tc32 == 2 && umma_ok(d, g, mode, 0))
       return run_umma_rowsum(BWD ? 2 : 1, d, g, N, 0, X, nullptr, W, var, ls, G, out, dW, dvar, dls, st);
   }
   if constexpr (std::is_same<T, double>::value) if (mma_path) {

@@ -402,8 +402,8 @@ __host__ __device__ inline Smem smem_plan(int KP, int HW, int P, int R) {  // R:
   o += 2 * (2 * 4 * KP * TN);
   s.wc = o;
   o += 4 * TN * 4;
-  s.img = o;  // 2 raw buffers (cp.async targets) + xh, xl, sh, sl, sq; then eh, el (P each)
-  o += 7 * ((HW * 4 + 15) / 16 * 16) + 2 * ((P * 4 + 15) / 16 * 16);
+  s.img = o;  // 3 raw buffers (cp.async ring), then a 3-deep ring of derived arrays: xh, xl, sh, sl (HW), eh, el (P)
+  o += 3 * ((HW * 4 + 15) / 16 * 16) + 3 * (4 * ((HW * 4 + 15) / 16 * 16) + 2 * ((P * 4 + 15) / 16 * 16));
   s.zbuf = o;  // two raw Z tiles (mode 0)
   o += 2 * TM * (KP - 2) * 4;
   s.w = o;
@@ -442,13 +442,9 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
   float* wc = reinterpret_cast<float*>(smem + L.wc);
   float* img0 = reinterpret_cast<float*>(smem + L.img);
   const int img_stride = (HW * 4 + 15) / 16 * 4;  // floats between consecutive image-sized arrays
-  float* xh = img0 + 2 * img_stride;              // pre-split pixels, plain ...
-  float* xl = img0 + 3 * img_stride;
-  float* sh = img0 + 4 * img_stride;              // ... and scaled by 2 c2
-  float* sl = img0 + 5 * img_stride;
-  float* sq = img0 + 6 * img_stride;              // squares (scratch of the norm pass)
-  float* eh = img0 + 7 * img_stride;              // e[p] = -c2 |x_p|^2, split
-  float* el = eh + (p.P * 4 + 15) / 16 * 4;
+  const int p_stride = (p.P * 4 + 15) / 16 * 4;
+  float* pre0 = img0 + 3 * img_stride;            // derived-array ring
+  const int pre_stride = 4 * img_stride + 2 * p_stride;
   float* zbuf = reinterpret_cast<float*>(smem + L.zbuf);
   float* w = reinterpret_cast<float*>(smem + L.w);
   float* racc = reinterpret_cast<float*>(smem + L.racc);
@@ -458,7 +454,9 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
   uint64_t* staged = bars;          // [2]
   uint64_t* mma_done = bars + 2;    // [2]
   uint64_t* tmem_empty = bars + 4;  // [2]
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* img_bar = bars + 6;     // [3] image ring: every producer's cp.async of the buffer has landed
+  uint64_t* pre_bar = bars + 9;     // [3] derived arrays of the image are complete
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mode = p.mode;
@@ -482,6 +480,10 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
       mbar_init(&mma_done[b], 1);
       mbar_init(&tmem_empty[b], kEpi / 32);
     }
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(&img_bar[b], kProd);
+      mbar_init(&pre_bar[b], kProd);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -502,12 +504,18 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
   if (warp < kProd / 32) {
     // ============================== producers
     const int pt = tid;
-    int cur_img = -1, pre_img = -1, ibuf = 0, akey = -1, bkey = -1, aslot = 1, bslot = 1;
-    auto fetch_image = [&](int n, int buf) {
+    int cur_img = -1, ki = -1, akey = -1, bkey = -1, aslot = 1, bslot = 1;
+    // Images stream through a three-deep cp.async ring with one mbarrier per buffer, and the arrays
+    // derived from an image (split pixels, split patch norms) through a second three-deep ring: a
+    // producer warp never meets the others at a CTA barrier (they run up to two units apart).
+    auto fetch_image = [&](int n, int k) {
       const float* src = p.X + (size_t)n * HW;
-      float* dst = img0 + buf * img_stride;
+      float* dst = img0 + (k % 3) * img_stride;
       for (int i = pt; i < HW; i += kProd) cp_async4(dst + i, src + i);
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&img_bar[k % 3])) : "memory");
     };
+    const float *xh = nullptr, *xl = nullptr, *sh = nullptr, *sl = nullptr, *eh = nullptr, *el = nullptr;
+    const int units_per_image = mode == 3 ? p.E2 : p.E1 * p.E2;
     UnitIter it;
     it.init(lo, p.E1, p.E2);
     // Z rows (mode 0: a new A tile every unit) are fetched one unit ahead with cp.async: no global-memory
@@ -523,44 +531,37 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
       const Unit un = decode(mode, it);
       if (pt == 0) CGP_TRACE(0, u);
       const bool needA = un.akey != akey, needB = un.bkey != bkey;
-      if (((needA && !a_is_z) || (needB && !b_is_z)) && un.n != cur_img) {
-        if (pre_img != un.n) {
-          cp_async_wait_all();   // a stale prefetch may target the same buffer
-          named_sync(1, kProd);  // nobody still reads the buffer about to be overwritten
-          ibuf ^= 1;
-          fetch_image(un.n, ibuf);
-        } else {
-          ibuf ^= 1;  // the prefetch went to the other buffer
-        }
-        cp_async_wait_all();
-        named_sync(1, kProd);  // image visible to every producer; everyone is past the previous image
+      // (with a single unit per image the rings are only safe once unit u-2 is fully staged by everyone)
+      if (units_per_image < 2 && u >= 2) mbar_wait(&mma_done[u & 1], ((u >> 1) - 1) & 1);
+      if (un.n != cur_img) {
+        if (ki < 0) fetch_image(un.n, 0);
         cur_img = un.n;
-        {  // split the pixels once per image; patch norms by a box sum of the squares
-          const float* raw = img0 + ibuf * img_stride;
-          for (int i = pt; i < HW; i += kProd) {
-            const float x = raw[i];
-            split_tf32(x, xh[i], xl[i]);
-            split_tf32(x * (2.f * c2), sh[i], sl[i]);
-            sq[i] = x * x;
-          }
-          named_sync(1, kProd);
-          for (int q = pt; q < p.P; q += kProd) {
-            const float* base = sq + (q / p.Wout) * p.Wd + (q % p.Wout);
-            float ss = 0.f;
-#pragma unroll
-            for (int i = 0; i < PH; ++i)
-#pragma unroll
-              for (int j = 0; j < PW; ++j) ss += base[i * p.Wd + j];
-            split_tf32(-c2 * ss, eh[q], el[q]);
-          }
-          named_sync(1, kProd);
-        }
-        // prefetch the image this CTA needs next (in-bounds even if it never gets there)
+        ++ki;
+        // the image this CTA needs next (in-bounds even if it never gets there); its buffer held image ki - 2
         const int nx = mode != 3 ? un.n + 1 : (un.n + 1 == p.N ? 0 : un.n + 1);
-        if (nx < p.N && nx != un.n) {
-          fetch_image(nx, ibuf ^ 1);
-          pre_img = nx;
+        fetch_image(nx < p.N ? nx : un.n, ki + 1);
+        mbar_wait(&img_bar[ki % 3], (ki / 3) & 1);
+        const float* raw = img0 + (ki % 3) * img_stride;
+        float* wxh = pre0 + (ki % 3) * pre_stride;
+        float *wxl = wxh + img_stride, *wsh = wxl + img_stride, *wsl = wsh + img_stride;
+        float *weh = wsl + img_stride, *wel = weh + p_stride;
+        for (int i = pt; i < HW; i += kProd) {
+          const float x = raw[i];
+          split_tf32(x, wxh[i], wxl[i]);
+          split_tf32(x * (2.f * c2), wsh[i], wsl[i]);
         }
+        for (int q = pt; q < p.P; q += kProd) {
+          const float* base = raw + (q / p.Wout) * p.Wd + (q % p.Wout);
+          float ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < PH; ++i)
+#pragma unroll
+            for (int j = 0; j < PW; ++j) ss = fmaf(base[i * p.Wd + j], base[i * p.Wd + j], ss);
+          split_tf32(-c2 * ss, weh[q], wel[q]);
+        }
+        mbar_arrive(&pre_bar[ki % 3]);
+        mbar_wait(&pre_bar[ki % 3], (ki / 3) & 1);
+        xh = wxh; xl = wxl; sh = wsh; sl = wsl; eh = weh; el = wel;
       }
       // The A row (registers) and the column weights are prepared BEFORE waiting for the operand
       // slots: only the TMEM / shared-memory stores sit in the MMA(u-2) -> stage -> MMA(u) loop.  Rows of
@@ -1079,7 +1080,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
         for (int it2 = 0; it2 < kPer; ++it2) {
           const int item = pt + it2 * kDzProd;
           if (item < kItems) {
-            const int oct = item % (TN / 8), d = item / (TN / 8);
+            const int d = item % D, oct = item / D;
             const int doff = (d / PW) * p.Wd + (d % PW);
             const int g0 = brow + oct * 8;
             if ((p.Wout & 7) == 0 && g0 + 8 <= p.P) {  // the octet lies in one patch row: 8 consecutive pixels
@@ -1124,7 +1125,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
         for (int it2 = 0; it2 < kPer; ++it2) {
           const int item = pt + it2 * kDzProd;
           if (item < kItems) {
-            const int oct = item % (TN / 8), d = item / (TN / 8);
+            const int d = item % D, oct = item / D;
             const int off = oct * (16 * 64) + (d >> 3) * 128 + (d & 7) * 16;
             *reinterpret_cast<uint4*>(bt + off) = make_uint4(q1[it2][0], q1[it2][1], q1[it2][2], q1[it2][3]);
             *reinterpret_cast<uint4*>(bt + off + 4 * 128) = make_uint4(q2[it2][0], q2[it2][1], q2[it2][2], q2[it2][3]);
