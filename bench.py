@@ -226,7 +226,8 @@ def run_gpu(args):
     import ctypes
     peaks = {}
     if rank == 0:
-        for kind, name in ((0, "fp64_fma"), (1, "fp32_fma"), (2, "mufu_ex2"), (3, "f64_exp"), (4, "fp64_mma"), (16, "tf32_mma")):
+        for kind, name in ((0, "fp64_fma"), (1, "fp32_fma"), (2, "mufu_ex2"), (3, "f64_exp"), (4, "fp64_mma"), (16, "tf32_mma"),
+                           (17, "tcgen05_tf32")):
             v = ctypes.c_double()
             _lib.check(_lib.lib().cgp_peak_probe(kind, ctypes.byref(v)))
             peaks[name] = v.value
@@ -404,20 +405,27 @@ def run_gpu(args):
         pipe, peak_note = "fp64", ("FP64 pipe: flops/(2*max(DFMA, DMMA) rate) + exps/(library exp rate), all probed on "
                                    "this GPU by cgp_peak_probe (MEASURED_PEAKS.json has no FP64 figure)")
     else:
-        fma32 = max(peaks["fp32_fma"], peaks["tf32_mma"] / 3.0)  # 3xTF32 split: three MMAs per float32 product
-
+        # float32 runs on three pipes at once: the contraction FMAs (2D of the 2D+2 / 2D+8 flops of a pair, 4D of
+        # the 4D+8 of a Kuf backward pair) on tcgen05 tensor cores at three TF32 MMAs per float32 product, the exps on
+        # MUFU, everything else on the FP32 FMA pipe.  The slowest of the three bounds the kernel.
         def t_bound(fl, ex):
-            return max(fl / (2 * fma32), ex / peaks["mufu_ex2"])
-        pipe, peak_note = "fp32", ("max(flops/(2*max(FFMA, TF32 mma.sync/3) rate), exps/MUFU ex2 rate), all probed on "
-                                   "this GPU by cgp_peak_probe")
+            per_pair = fl / ex
+            contraction = ex * (4 * D if per_pair > 3 * D else 2 * D)
+            return max(3 * (contraction / 2) / peaks["tcgen05_tf32"], ex / peaks["mufu_ex2"],
+                       (fl - contraction) / (2 * peaks["fp32_fma"]))
+        pipe, peak_note = "mufu", ("max(3 * contraction FMAs / tcgen05 kind::tf32 rate, exps / MUFU ex2 rate, remaining flops / "
+                                   "(2 * FFMA rate)): the three pipes run concurrently; MUFU binds at this shape.  All rates "
+                                   "probed on this GPU by cgp_peak_probe")
     dom = max(per_kernel, key=per_kernel.get)
     fl, ex = work[dom]
+    if args.dtype != "f64":  # the step bound is the sum of the per-kernel bounds (each kernel has its own binding pipe)
+        step_bound = sum(t_bound(*work[k]) for k in work if k != "step")
     dur = per_kernel[dom] * 1e-3
     achieved = fl / dur / 1e12
     peak = fl / t_bound(fl, ex) / 1e12
     sfl, sex = work["step"]
     ms_per_step = total_ms / args.steps
-    step_frac = t_bound(sfl, sex) / (ms_per_step * 1e-3)
+    step_frac = (t_bound(sfl, sex) if args.dtype == "f64" else step_bound) / (ms_per_step * 1e-3)
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]

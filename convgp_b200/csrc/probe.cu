@@ -2,6 +2,7 @@
 // runs independent dependent-chains long enough to saturate one pipe on every SM and reports
 // operations per second (an FMA counts as ONE operation).
 #include "common.cuh"
+#include "umma32.cuh"
 
 namespace cgp {
 
@@ -227,6 +228,69 @@ static int run_probe(double ops_per_thread_iter, double* result) {
 
 }  // namespace cgp
 
+// tcgen05.mma kind::tf32 throughput: every SM issues `iters` MMAs of M=128, N=256, K=8 (operands
+// in shared memory, accumulator in TMEM) from one thread; FMAs per second over the whole chip.
+__global__ void __launch_bounds__(128, 1) tcgen05_probe_kernel(int iters) {
+  using namespace cgp::umma;
+  extern __shared__ __align__(128) unsigned char sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (4096 + 8192) / 4; i += 128) reinterpret_cast<float*>(sm)[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base_s;
+  if (tid == 0) {
+    constexpr uint32_t idesc = make_idesc(128, 256, kFmtTF32);
+    const uint64_t da = make_desc(smem_u32(sm), 16 * 128, 128), db = make_desc(smem_u32(sm + 4096), 16 * 256, 128);
+    for (int r = 0; r < iters / 16; ++r) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mma_tf32_ss(tb, da, db, idesc, 1);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(256) : "memory");
+}
+
+static int run_tcgen05_probe(double* ops_per_s) {
+  using namespace cgp;
+  const int iters = 4096, sms = num_sms();
+  const size_t smem = 4096 + 8192;
+  cudaEvent_t a, b;
+  CGP_CUDA_CHECK(cudaEventCreate(&a));
+  CGP_CUDA_CHECK(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CGP_CUDA_CHECK(cudaEventRecord(a));
+    tcgen05_probe_kernel<<<sms, 128, smem>>>(iters);
+    CGP_CUDA_CHECK(cudaEventRecord(b));
+    CGP_CUDA_CHECK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CGP_CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  CGP_CUDA_CHECK(cudaGetLastError());
+  *ops_per_s = (double)sms * iters * 128.0 * 256.0 * 8.0 / (best * 1e-3);
+  return CGP_OK;
+}
+
 extern "C" int cgp_peak_probe(int32_t kind, double* ops_per_s) {
   using namespace cgp;
   if (!ops_per_s) {
@@ -258,6 +322,8 @@ extern "C" int cgp_peak_probe(int32_t kind, double* ops_per_s) {
     case 15: return run_probe<15>(kChains * 8.0, ops_per_s);
     // one m16n8k8 mma = 1024 FMAs per warp = 32 per thread
     case 16: return run_probe<16>(kChains * 32.0, ops_per_s);
+    // tcgen05.mma kind::tf32 (UMMA), FMAs per second
+    case 17: return run_tcgen05_probe(ops_per_s);
     default:
       set_error("unknown probe kind %d", kind);
       return CGP_ERR_BAD_DESC;

@@ -400,8 +400,8 @@ __host__ __device__ inline Smem smem_plan(int KP, int HW, int P, int R) {  // R:
   int o = 0;
   s.sB = o;
   o += 2 * (2 * 4 * KP * TN);
-  s.wc = o;
-  o += 4 * TN * 4;
+  s.wc = o;  // column weights, eight-deep ring (see the producer loop)
+  o += 8 * TN * 4;
   s.img = o;  // 3 raw buffers (cp.async ring), then a 3-deep ring of derived arrays: xh, xl, sh, sl (HW), eh, el (P)
   o += 3 * ((HW * 4 + 15) / 16 * 16) + 3 * (4 * ((HW * 4 + 15) / 16 * 16) + 2 * ((P * 4 + 15) / 16 * 16));
   s.zbuf = o;  // two raw Z tiles (mode 0)
@@ -585,7 +585,9 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
         nx.next();
         fetch_zrow(decode(mode, nx).arow + pt, (u + 1) & 1);
       }
-      // column weights of this unit (four buffers: the epilogue of unit u-4 is certainly over)
+      // column weights of this unit.  Written before the slot wait below, when only the wait of unit u-1 is
+      // behind us: MMA(u-3) was issued, hence the epilogue of unit u-5 is over -> an eight-deep ring
+      // (a four-deep one let the epilogue of unit u-4 read the next tile's weights)
       if (pt >= kProd - TN) {
         const int c = pt - (kProd - TN), col = un.brow + c;
         float v = 0.f;
@@ -594,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
         } else if (col < p.P) {
           v = w[col];
         }
-        wc[(u & 3) * TN + c] = v;
+        wc[(u & 7) * TN + c] = v;
       }
       if (pt == 32) CGP_TRACE(9, u);
       if (u >= 2) mbar_wait(&mma_done[u & 1], ((u >> 1) - 1) & 1);  // the MMAs of unit u-2 have read their operands
@@ -756,7 +758,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
       if (lane == 0 && half == 0) CGP_TRACE(20 + quarter, u);
       tc_fence_after();
       const uint32_t taddr = lane_addr + (uint32_t)(u & 1) * TN;
-      const float4* wc4 = reinterpret_cast<const float4*>(wc + (u & 3) * TN + half * (TN / 2));
+      const float4* wc4 = reinterpret_cast<const float4*>(wc + (u & 7) * TN + half * (TN / 2));
       uint32_t va[32], vb[32];
       auto process = [&](uint32_t (&v)[32], int c0) {
 #pragma unroll

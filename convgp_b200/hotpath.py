@@ -37,7 +37,8 @@ class HotPath:
         self.dZ, self.dW, self.dvar, self.dls = views
         self.ws, self.ws_bytes = spec.workspace(N, M, dev)
         self.graph = None
-        self.kernels_per_step = 6
+        # Kuf / Kdiag / Kuu forward + backward; the float32 Kuf backward is two kernels (dZ part + dW pass)
+        self.kernels_per_step = 7 if dt == torch.float32 else 6
 
     def forward(self):
         L, s, st = _lib.lib(), self.spec, stream_ptr()

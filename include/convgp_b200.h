@@ -116,7 +116,8 @@ int cgp_kfull_fwd(const cgp_kernel_desc* d, int32_t N, int32_t N2, const void* X
 /* Pipe-throughput probes used by bench.py for the compute roofline: runs a
  * dependent-chain micro-kernel on the current device, synchronises, and returns operations per
  * second in *ops_per_s.  kind: 0 = FP64 FMA, 1 = FP32 FMA, 2 = MUFU ex2.approx.f32,
- * 3 = this library's double-precision exp, 4 = FP64 mma.sync m8n8k4 (counted as FMAs). */
+ * 3 = this library's double-precision exp, 4 = FP64 mma.sync m8n8k4 (counted as FMAs),
+ * 16 = TF32 mma.sync m16n8k8, 17 = tcgen05.mma kind::tf32 (FMAs per second). */
 int cgp_peak_probe(int32_t kind, double* ops_per_s);
 
 #ifdef __cplusplus

@@ -1,4 +1,4 @@
-"""Both kernel families of each dtype (float64: FP64-MMA / scalar FMA; float32: 3xTF32 tensor-core /
+"""Every kernel family of each dtype (float64: FP64-MMA / scalar FMA; float32: tcgen05 UMMA / 3xTF32 mma.sync /
 scalar FMA) must pass parity whatever the library's default selection is: re-run the parity, golden
 and identity tests in subprocesses with the selection forced."""
 import os
@@ -11,11 +11,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("family", ["mma", "fma"])
+@pytest.mark.parametrize("family", ["umma", "mma", "fma"])
 def test_forced_kernel_family(family):
     env = dict(os.environ)
     for k in ("CGP_KUF_FWD", "CGP_KUF_BWD", "CGP_KDIAG_FWD", "CGP_KDIAG_BWD"):
-        env[k] = family
+        env[k] = "mma" if family == "umma" else family  # float64 has no UMMA family (no FP64 tcgen05 kind)
         env[k + "_F32"] = family
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "tests/test_gpu_parity.py",
                         "tests/test_golden.py", "tests/test_gpu_identities.py", "-p", "no:cacheprovider"],
