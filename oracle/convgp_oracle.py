@@ -8,20 +8,27 @@ product package ``convgp_b200`` never does.
 
 Pinning status
 --------------
-The reference (TensorFlow 1.x + the un-vendored ``GPflow-inter-domain`` fork, no version
-pinned anywhere in /root/reference) cannot be installed in this image, and its tests hold
-no golden vectors, only identities.  The oracle is therefore
-pinned by
+The reference's stack (TensorFlow 1.x + the un-vendored ``GPflow-inter-domain`` fork, no version
+pinned anywhere in /root/reference) cannot be installed in this image, and its tests hold no
+golden vectors, only identities.  The oracle is pinned by
 
+* **outputs of the reference's own source**: /root/reference/convgp/{convkernels,misvgp,svsumgp,
+  svconvgp}.py are imported unmodified on top of stand-ins for the 27 ``tf.*`` calls and the GPflow
+  classes they use (oracle/ref_shim/, oracle/run_reference.py).  The reference's own unit tests
+  (testing/test_convkerns.py, 9 tests) pass on those stand-ins (tests/test_reference_source.py), and
+  the vectors that code produces -- values, and autodiff gradients through it -- are committed as
+  tests/golden/ref/*.npz (tests/golden/make_ref_golden.py).  This oracle reproduces them to 1e-12
+  (tests/test_ref_golden.py): every kernel class, both patch layouts, K / Kdiag / Kzx / Kzz, the
+  in-tree ``conditional``, and the build_predict of the four model classes;
 * the in-tree spelled-out RBF form in ``ConvRBF.Kzx`` (convkernels.py:211-225), which the
   reference's own test T1 (testing/test_convkerns.py:33-39) requires to equal
   ``Conv(RBF).Kzx`` -- this fixes ``RBF.K`` = variance * exp(-(|x|^2 - 2 x.z + |z|^2) / (2 l^2));
-* identities T2-T8 (testing/test_convkerns.py:51-140) and T9 (testing/test_svsumgp.py);
-* the in-tree copy of ``conditional`` (misvgp.py:83-165).
+* identities T2-T8 (testing/test_convkerns.py:51-140) and T9 (testing/test_svsumgp.py).
 
 Semantics that live only in the absent GPflow fork (``Add.Kzx/Kzz``, ``White``, the
 ``positive`` transform, likelihood quadratures, ``gauss_kl_white``) are restated from the
-published GPflow 0.x algorithm and are **parity unpinned** by anything in /root/reference.
+published GPflow 0.x algorithm -- in the stand-ins as well as here -- and are **parity unpinned**
+by anything in /root/reference.
 """
 import numpy as np
 
