@@ -356,9 +356,8 @@ def run_gpu(args):
             _lib.check(L.cgp_kuf_fwd(s.ref(), hp.N, hp.M, p(hp.X), p(hp.Z), p(hp.W), p(hp.variance), p(hp.lengthscales),
                                      p(hp.Kuf), None, 0, st()))
 
-        def k_kdiag_fwd():
-            _lib.check(L.cgp_kdiag_fwd(s.ref(), hp.N, p(hp.X), p(hp.W), p(hp.variance), p(hp.lengthscales),
-                                       p(hp.Kdiag), None, 0, st()))
+        def k_kdiag_fwd():  # the forward that stores the per-image row sums its backward is made of, when covered
+            hp._kdiag_fwd(st())
 
         def k_kuu_fwd():
             _lib.check(L.cgp_kuu_fwd(s.ref(), hp.M, p(hp.Z), p(hp.variance), p(hp.lengthscales), hp.diag_add,
@@ -369,8 +368,7 @@ def run_gpu(args):
                                      p(hp.G), p(hp.dZ), p(hp.dW), p(hp.dvar), p(hp.dls), None, 0, st()))
 
         def k_kdiag_bwd():
-            _lib.check(L.cgp_kdiag_bwd(s.ref(), hp.N, p(hp.X), p(hp.W), p(hp.variance), p(hp.lengthscales), p(hp.gd),
-                                       p(hp.dW), p(hp.dvar), p(hp.dls), None, 0, st()))
+            hp._kdiag_bwd(st())
 
         def k_kuu_bwd():
             _lib.check(L.cgp_kuu_bwd(s.ref(), hp.M, p(hp.Z), p(hp.variance), p(hp.lengthscales), p(hp.Gu), p(hp.dZ),

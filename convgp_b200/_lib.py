@@ -18,7 +18,7 @@ OUT_SUM, OUT_PER_CHANNEL = 0, 1
 EXPORTS = [
     "cgp_version", "cgp_last_error", "cgp_status_string", "cgp_geometry", "cgp_workspace_bytes", "cgp_patches",
     "cgp_kuf_fwd", "cgp_kuf_bwd", "cgp_kdiag_fwd", "cgp_kdiag_bwd", "cgp_kuu_fwd", "cgp_kuu_bwd",
-    "cgp_kfull_fwd", "cgp_peak_probe",
+    "cgp_kfull_fwd", "cgp_peak_probe", "cgp_kdiag_saved_elems", "cgp_kdiag_fwd_saved", "cgp_kdiag_bwd_saved",
 ]
 
 
@@ -64,6 +64,10 @@ def lib():
     L.cgp_kuf_bwd.argtypes = [dp, i32, i32] + [vp] * 10 + [vp, sz, vp]
     L.cgp_kdiag_fwd.argtypes = [dp, i32] + [vp] * 5 + [vp, sz, vp]
     L.cgp_kdiag_bwd.argtypes = [dp, i32] + [vp] * 8 + [vp, sz, vp]
+    L.cgp_kdiag_saved_elems.restype = sz
+    L.cgp_kdiag_saved_elems.argtypes = [dp, i32]
+    L.cgp_kdiag_fwd_saved.argtypes = [dp, i32] + [vp] * 6 + [sz, vp]
+    L.cgp_kdiag_bwd_saved.argtypes = [dp, i32] + [vp] * 4 + [sz] + [vp] * 4
     L.cgp_kuu_fwd.argtypes = [dp, i32, vp, vp, vp, dbl, vp, vp]
     L.cgp_kuu_bwd.argtypes = [dp, i32] + [vp] * 7 + [vp]
     L.cgp_kfull_fwd.argtypes = [dp, i32, i32] + [vp] * 6 + [vp, sz, vp]

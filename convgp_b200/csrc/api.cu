@@ -265,9 +265,10 @@ static bool umma_ok(const cgp_kernel_desc* d, const Geo& g, int mode, int M) {
 // mode: 0 Kuf fwd, 1 Kdiag fwd, 2 Kdiag bwd, 3 dW of Kuf (umma32.cuh)
 static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int N, int M, const void* X,
                            const void* Z, const void* W, const void* var, const void* ls, const void* G, void* out,
-                           void* dW, void* dvar, void* dls, cudaStream_t st) {
+                           void* dW, void* dvar, void* dls, cudaStream_t st, void* save = nullptr) {
   umma::Params p;
   memset(&p, 0, sizeof(p));
+  p.save = (float*)save;
   p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
   p.ls = (const float*)ls; p.G = (const float*)G; p.out = (float*)out; p.dW = (float*)dW;
   p.dvar = (float*)dvar; p.dls = (float*)dls;
@@ -306,7 +307,8 @@ static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int
   CGP_CUDA_CHECK(cudaGetDevice(&dev));
 #define CALL(PH_, PW_)                                                                                        \
   {                                                                                                           \
-    auto kernel = mode == 2 ? umma::rowsum_kernel<PH_, PW_, true> : umma::rowsum_kernel<PH_, PW_, false>;     \
+    auto kernel = (mode == 2 || mode == 4) ? umma::rowsum_kernel<PH_, PW_, true>                              \
+                                           : umma::rowsum_kernel<PH_, PW_, false>;                            \
     {                                                                                                         \
       std::lock_guard<std::mutex> lk(g_launch_mu);                                                            \
       size_t& cur = g_launch_smem[std::make_pair((const void*)kernel, dev)];                                  \
@@ -503,6 +505,90 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
 #define CALL(PH_, PW_) return launch_fast(kdiag_fast_kernel<T, PH_, PW_, BWD>, p, tpb, smem, st, "kdiag")
   CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL
+}
+
+// ---- Kdiag forward that keeps what its backward needs (cgp_kdiag_fwd_saved / cgp_kdiag_bwd_saved) ---------------
+// Per image n the backward of Kdiag is made of three things the forward sweep already touches:
+//   r[n, q] = sum_q' w_q' k(q, q')      -> dW[q]   += 2 var / P^2 * g[n] * r[n, q]
+//   v[n]    = sum_q w_q r[n, q]         -> dvar    += g[n] / P^2 * v[n]          (Kdiag[n] = var / P^2 * v[n])
+//   v2[n]   = sum w_q w_q' k * arg      -> dls     += -2 var / l * g[n] / P^2 * v2[n] / arg_scale
+// so a forward that stores them (N * (P + 2) elements) makes the backward O(N P) instead of O(N P^2 D).
+// Supported by the default family of each dtype (float32: tcgen05 row-sum kernel, float64: FP64 warp-MMA kernel)
+// when the image is one pairing domain with one RBF; otherwise the caller keeps the two-pass pair.
+static bool kdiag_saved_ok(const cgp_kernel_desc* d, const Geo& g, int mode) {
+  if (mode != 1 || d->out_mode == CGP_OUT_PER_CHANNEL) return false;
+  if (d->dtype == CGP_F32)
+    return env_choice("CGP_KDIAG_FWD_F32", 2) == 2 && env_choice("CGP_KDIAG_BWD_F32", 2) == 2 && umma_ok(d, g, mode, 0);
+  return env_choice("CGP_KDIAG_FWD", 1) != 0 && env_choice("CGP_KDIAG_BWD", 1) != 0;
+}
+
+template <typename T>
+static int run_kdiag_saved_fwd(const cgp_kernel_desc* d, const Geo& g, int mode, int N, const void* X, const void* W,
+                               const void* var, const void* ls, void* out, void* save, cudaStream_t st) {
+  CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(T) * (size_t)N, st));
+  CGP_CUDA_CHECK(cudaMemsetAsync(save, 0, sizeof(T) * (size_t)N * (g.P + 2), st));
+  if constexpr (std::is_same<T, float>::value) {
+    return run_umma_rowsum(4, d, g, N, 0, X, nullptr, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st, save);
+  } else {
+    FastParams<T> p;
+    fill_fast(p, d, g, mode, N, 0);
+    p.X = (const T*)X; p.Wt = (const T*)W; p.var = (const T*)var; p.ls = (const T*)ls;
+    p.out = (T*)out; p.save = (T*)save;
+    p.ndom = 1;
+    const int Pd = d->C * g.Pc;
+    static const int max_warps_env = env_choice("CGP_KDIAG_WARPS", 0);
+    const int max_warps = max_warps_env > 0 ? max_warps_env : 2;
+    const int tpb = 32 * pick_warps(Pd, std::min(3, max_warps), max_warps);
+    const int nchunk = (Pd + tpb - 1) / tpb;
+    const int Lsweep = std::min(Pd, Pd / 2 + 32);
+    const int noct = (Lsweep + 7) / 8;
+    p.S = (noct + kOctBlock - 1) / kOctBlock;
+    p.n_items = (long long)N * nchunk * p.S;
+    const size_t smem_m = mma_smem(p, true);
+#define CALL(PH_, PW_) return launch_fast(kdiag_mma_kernel<PH_, PW_, true>, p, tpb, smem_m, st, "kdiag")
+    CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+  }
+}
+
+// grid (ceil(P / 256), image chunks): thread q sums g[n] r[n, q] over its chunk of images (coalesced in q)
+template <typename T>
+__global__ void kdiag_bwd_saved_kernel(int N, int P, const T* __restrict__ g, const T* __restrict__ save,
+                                       const T* __restrict__ var, const T* __restrict__ ls, T* dW, T* dvar, T* dls,
+                                       T P2, T arg_scale) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = (N + gridDim.y - 1) / gridDim.y, n0 = blockIdx.y * per, n1 = min(N, n0 + per);
+  const T sig2 = var[0], lsv = ls[0];
+  if (q < P && dW) {
+    T acc = T(0);
+    for (int n = n0; n < n1; ++n) acc = fma_t(g[n], save[(size_t)n * P + q], acc);
+    atomicAdd(dW + q, T(2) * sig2 / P2 * acc);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {  // the two scalar gradients: one warp per image chunk
+    T a = T(0), b = T(0);
+    for (int n = n0 + (int)threadIdx.x; n < n1; n += 32) {
+      a = fma_t(g[n], save[(size_t)N * P + n], a);
+      b = fma_t(g[n], save[(size_t)N * P + N + n], b);
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (threadIdx.x == 0) {
+      if (dvar) atomicAdd(dvar, a / P2);
+      if (dls) atomicAdd(dls, T(-2) * sig2 / lsv * b / P2 / arg_scale);
+    }
+  }
+}
+
+template <typename T>
+static int run_kdiag_saved_bwd(const Geo& g, int N, const void* gK, const void* save, const void* var, const void* ls,
+                               void* dW, void* dvar, void* dls, cudaStream_t st) {
+  const int tpb = 256;
+  dim3 grid((g.P + tpb - 1) / tpb, std::max(1, std::min(N, 32)));
+  kdiag_bwd_saved_kernel<T><<<grid, tpb, 0, st>>>(N, g.P, (const T*)gK, (const T*)save, (const T*)var, (const T*)ls,
+                                                  (T*)dW, (T*)dvar, (T*)dls, (T)((double)g.P * (double)g.P),
+                                                  (T)Math<T>::kArgScale);
+  CGP_CUDA_CHECK(cudaGetLastError());
+  return CGP_OK;
 }
 
 template <typename T, bool BWD>
@@ -714,6 +800,53 @@ int cgp_kdiag_bwd(const cgp_kernel_desc* d, int32_t N, const void* X, const void
   }
   return generic_kxx(d, g.P, g.D, N, 0, X, nullptr, W, variance, lengthscales, gK, nullptr, dW, dvariance,
                      dlengthscales, /*diag_only=*/true, ws, ws_bytes, st);
+}
+
+size_t cgp_kdiag_saved_elems(const cgp_kernel_desc* d, int32_t N) {
+  Geo g;
+  if (geometry(d, &g) != CGP_OK || N < 1) return 0;
+  const int mode = fast_mode(d, g);
+  if (!mode || !kdiag_saved_ok(d, g, mode)) return 0;
+  return (size_t)N * (g.P + 2);
+}
+
+int cgp_kdiag_fwd_saved(const cgp_kernel_desc* d, int32_t N, const void* X, const void* W, const void* variance,
+                        const void* lengthscales, void* Kdiag, void* saved, size_t saved_elems, void* stream) {
+  Geo g;
+  CGP_TRY(geometry(d, &g));
+  if (N < 0) { set_error("negative N"); return CGP_ERR_BAD_DESC; }
+  if (N == 0) return CGP_OK;
+  CGP_NEED(X); CGP_NEED(variance); CGP_NEED(lengthscales); CGP_NEED(Kdiag); CGP_NEED(saved);
+  const int mode = fast_mode(d, g);
+  if (!mode || !kdiag_saved_ok(d, g, mode)) {
+    set_error("kdiag_fwd_saved: configuration not covered (cgp_kdiag_saved_elems returns 0): use cgp_kdiag_fwd/bwd");
+    return CGP_ERR_UNSUPPORTED;
+  }
+  if (saved_elems < (size_t)N * (g.P + 2)) { set_error("kdiag_fwd_saved: saved buffer too small"); return CGP_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == CGP_F64)
+    return run_kdiag_saved_fwd<double>(d, g, mode, N, X, W, variance, lengthscales, Kdiag, saved, st);
+  return run_kdiag_saved_fwd<float>(d, g, mode, N, X, W, variance, lengthscales, Kdiag, saved, st);
+}
+
+int cgp_kdiag_bwd_saved(const cgp_kernel_desc* d, int32_t N, const void* variance, const void* lengthscales,
+                        const void* gK, const void* saved, size_t saved_elems, void* dW, void* dvariance,
+                        void* dlengthscales, void* stream) {
+  Geo g;
+  CGP_TRY(geometry(d, &g));
+  if (N < 0) { set_error("negative N"); return CGP_ERR_BAD_DESC; }
+  if (N == 0) return CGP_OK;
+  CGP_NEED(variance); CGP_NEED(lengthscales); CGP_NEED(gK); CGP_NEED(saved);
+  const int mode = fast_mode(d, g);
+  if (!mode || !kdiag_saved_ok(d, g, mode)) {
+    set_error("kdiag_bwd_saved: configuration not covered (cgp_kdiag_saved_elems returns 0)");
+    return CGP_ERR_UNSUPPORTED;
+  }
+  if (saved_elems < (size_t)N * (g.P + 2)) { set_error("kdiag_bwd_saved: saved buffer too small"); return CGP_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == CGP_F64)
+    return run_kdiag_saved_bwd<double>(g, N, gK, saved, variance, lengthscales, dW, dvariance, dlengthscales, st);
+  return run_kdiag_saved_bwd<float>(g, N, gK, saved, variance, lengthscales, dW, dvariance, dlengthscales, st);
 }
 
 int cgp_kuu_fwd(const cgp_kernel_desc* d, int32_t M, const void* Z, const void* variance,

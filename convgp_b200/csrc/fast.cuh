@@ -27,6 +27,7 @@ struct FastParams {
   T* dW;
   T* dvar;
   T* dls;
+  T* save;  // Kdiag forward-with-residuals (mma64.cuh): [N * Pd] row sums, [N] sum w r, [N] sum w w k arg
   int N, M, H, Wd, C, Hout, Wout, Pc;
   int Dtot;             // elements per Z row
   int zstride, zplane;  // Z[m, c*zplane + d*zstride] is element d of plane c's reference patch

@@ -444,7 +444,10 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lc = lane & 3;
-  const bool do_dw = BWD && p.dW != nullptr;
+  // SAVE: the forward that leaves its backward's ingredients behind (cgp_kdiag_fwd_saved): the backward sweep
+  // with unit upstream gradients, per-image row sums flushed to p.save instead of a gradient buffer
+  const bool SAVE = BWD && p.save != nullptr;
+  const bool do_dw = BWD && (p.dW != nullptr || SAVE);
   Math<T>::init_table(tbl);
   for (int i = tid; i < nW; i += blockDim.x) {
     w[i] = p.Wt ? p.Wt[i] : T(1);
@@ -501,19 +504,25 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
       v = block_sum(v, red);
       if (tid == 0) atomicAdd(p.out + o, v * sig2 / P2);
     } else {
-      const T gn = p.G[o] / P2;
+      const T gn = SAVE ? T(0) : p.G[o] / P2;
       v = block_sum(v, red);
       v2 = block_sum(v2, red);
       if (tid == 0) {
-        if (p.dvar) atomicAdd(p.dvar + g, gn * v);
-        if (p.dls) atomicAdd(p.dls + g, T(-2) * sig2 / lsg * gn * v2);
+        if (SAVE) {
+          atomicAdd(p.out + o, v * sig2 / P2);
+          atomicAdd(p.save + (size_t)p.N * Pd + kn, v);
+          atomicAdd(p.save + (size_t)p.N * Pd + p.N + kn, v2);
+        } else {
+          if (p.dvar) atomicAdd(p.dvar + g, gn * v);
+          if (p.dls) atomicAdd(p.dls + g, T(-2) * sig2 / lsg * gn * v2);
+        }
       }
       if (do_dw) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const T d = quad_sum(dwown[t]);
           if (lc == 0 && own[t] < Pd)
-            atomicAdd(dWacc + (p.w_per_plane ? cb * p.Pc : 0) + own[t], T(2) * sig2 * gn * d);
+            atomicAdd(dWacc + (p.w_per_plane ? cb * p.Pc : 0) + own[t], SAVE ? d : T(2) * sig2 * gn * d);
         }
       }
     }
@@ -549,6 +558,14 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
       if (cur_key >= 0) flush();
       if (n != cur_img) {
         __syncthreads();
+        if (SAVE && cur_img >= 0) {  // row sums of the finished image (one pairing domain, checked by the host)
+          for (int i = tid; i < nW; i += blockDim.x) {
+            const T v = dWacc[i];
+            dWacc[i] = T(0);
+            if (v != T(0)) atomicAdd(p.save + (size_t)cur_img * Pd + i, v);
+          }
+          __syncthreads();
+        }
         stage_image<T, PH, PW>(p, n, img, e);
         cur_img = n;
       }
@@ -579,7 +596,7 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
     T gs = T(0);
     if constexpr (BWD) {
       const size_t o = p.out_per_channel ? (size_t)n * p.C + dm : (size_t)n;
-      gs = T(2) * sig2 * p.G[o] / P2;
+      gs = SAVE ? T(1) : T(2) * sig2 * p.G[o] / P2;
     }
     // INTERIOR octets: every (own row, column) pair of the tile has 0 < delta < P/2, i.e. weight 2
     // and no masks -- all but the first four and last four octets of a warp's sweep.
@@ -679,9 +696,10 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
   if (cur_key >= 0) flush();
   if (do_dw) {
     __syncthreads();
+    T* dst = SAVE ? p.save + (size_t)max(cur_img, 0) * Pd : p.dW;
     for (int i = tid; i < nW; i += blockDim.x) {
       T v = dWacc[i];
-      if (v != T(0)) atomicAdd(p.dW + i, v);
+      if (v != T(0)) atomicAdd(dst + i, v);
     }
   }
 }

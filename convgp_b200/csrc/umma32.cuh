@@ -18,11 +18,13 @@
 // layout), warp 8 lane 0 issues the MMAs.  mbarriers: staged[2] (producers -> issuer),
 // mma_done[2] (tcgen05.commit -> epilogue and producers), tmem_empty[2] (epilogue -> issuer).
 //
-// One kernel, four uses ("row-sum" modes; rows = TMEM lanes, columns weighted and summed):
+// One kernel, five uses ("row-sum" modes; rows = TMEM lanes, columns weighted and summed):
 //   0  Kuf forward   rows = inducing patches, cols = patches of image n, weights w_p
 //   1  Kdiag forward rows = patches of image n, cols = patches of image n, weights w_p'
 //   2  Kdiag backward: same tiles, also accumulates sum_c w_c k S for dlengthscale
 //   3  dW of Kuf     rows = patches of image n, cols = inducing patches, weights G[m, n]
+//   4  Kdiag forward that also saves, per image, the row sums and the two totals its backward is made of
+//      (api.cu: cgp_kdiag_fwd_saved / cgp_kdiag_bwd_saved) -- the backward then never revisits the P x P Gram
 // and a second kernel (kuf_dz_kernel) for the dZ / dvariance / dlengthscale part of Kuf backward,
 // which feeds the coefficients back through TMEM as the A operand of a second GEMM.
 #pragma once
@@ -46,6 +48,7 @@ struct Params {
   float* dW;
   float* dvar;
   float* dls;
+  float* save;  // mode 4: [N * P] row sums r[n, q] = sum_c w_c k(q, c), then [N] sum_q w_q r, then [N] sum w w k S
   int N, M, H, Wd, Hout, Wout, P, D;
   int mode;
   int E1, E2;  // extents of the middle / inner unit coordinates
@@ -121,6 +124,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(a), "r"(parity)
         : "memory");
+#if defined(CGP_MBAR_SLEEP) && CGP_MBAR_SLEEP > 0
+    if (!done) __nanosleep(CGP_MBAR_SLEEP);  // back off: every poll is an op in the shared-memory (MIO) queue
+#endif
   } while (!done);
 #endif
 }
@@ -732,10 +738,19 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
         v2 = fmaf(w[q], a2, v2);
         racc[q] = racc[2 * Pp + q] = racc[Pp + q] = racc[3 * Pp + q] = 0.f;
         if (mode == 2 && p.dW) atomicAdd(p.dW + q, 2.f * s_kd * gn * a1);
+        if (mode == 4) atomicAdd(p.save + (size_t)img_n * p.P + q, a1);  // an image can be shared by two CTAs
       }
       if (mode == 1) {
         const float v = epi_sum(v1);
         if (et == 0) atomicAdd(p.out + img_n, v * s_kd);
+      } else if (mode == 4) {
+        const float v = epi_sum(v1);
+        const float vv = epi_sum(v2);
+        if (et == 0) {
+          atomicAdd(p.out + img_n, v * s_kd);
+          atomicAdd(p.save + (size_t)p.N * p.P + img_n, v);
+          atomicAdd(p.save + (size_t)p.N * p.P + p.N + img_n, vv);
+        }
       } else {
         tvar = fmaf(gn / P2, v1, tvar);
         tls = fmaf(gn / P2, v2, tls);

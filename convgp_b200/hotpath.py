@@ -36,6 +36,10 @@ class HotPath:
             o += s
         self.dZ, self.dW, self.dvar, self.dls = views
         self.ws, self.ws_bytes = spec.workspace(N, M, dev)
+        # Kdiag: the forward stores the per-image row sums its backward is made of (N * (P + 2) elements) when
+        # the configuration is covered, and the backward is then O(N P) instead of a second sweep of the Gram
+        n_saved = _lib.lib().cgp_kdiag_saved_elems(spec.ref(), N) if N > 0 else 0
+        self.kd_saved = torch.empty(n_saved, dtype=dt, device=dev) if n_saved else None
         self.graph = None
         # Kuf / Kdiag / Kuu forward + backward; the float32 Kuf backward is two kernels (dZ part + dW pass)
         self.kernels_per_step = 7 if dt == torch.float32 else 6
@@ -44,10 +48,30 @@ class HotPath:
         L, s, st = _lib.lib(), self.spec, stream_ptr()
         check(L.cgp_kuf_fwd(s.ref(), self.N, self.M, ptr(self.X), ptr(self.Z), ptr(self.W), ptr(self.variance),
                             ptr(self.lengthscales), ptr(self.Kuf), ptr(self.ws), self.ws_bytes, st))
-        check(L.cgp_kdiag_fwd(s.ref(), self.N, ptr(self.X), ptr(self.W), ptr(self.variance), ptr(self.lengthscales),
-                              ptr(self.Kdiag), ptr(self.ws), self.ws_bytes, st))
+        self._kdiag_fwd(st)
         check(L.cgp_kuu_fwd(s.ref(), self.M, ptr(self.Z), ptr(self.variance), ptr(self.lengthscales), self.diag_add,
                             ptr(self.Kuu), st))
+
+    def _kdiag_fwd(self, st):
+        L, s = _lib.lib(), self.spec
+        if self.kd_saved is not None:
+            check(L.cgp_kdiag_fwd_saved(s.ref(), self.N, ptr(self.X), ptr(self.W), ptr(self.variance),
+                                        ptr(self.lengthscales), ptr(self.Kdiag), ptr(self.kd_saved),
+                                        self.kd_saved.numel(), st))
+        else:
+            check(L.cgp_kdiag_fwd(s.ref(), self.N, ptr(self.X), ptr(self.W), ptr(self.variance),
+                                  ptr(self.lengthscales), ptr(self.Kdiag), ptr(self.ws), self.ws_bytes, st))
+
+    def _kdiag_bwd(self, st):
+        L, s = _lib.lib(), self.spec
+        if self.kd_saved is not None:
+            check(L.cgp_kdiag_bwd_saved(s.ref(), self.N, ptr(self.variance), ptr(self.lengthscales), ptr(self.gd),
+                                        ptr(self.kd_saved), self.kd_saved.numel(), ptr(self.dW), ptr(self.dvar),
+                                        ptr(self.dls), st))
+        else:
+            check(L.cgp_kdiag_bwd(s.ref(), self.N, ptr(self.X), ptr(self.W), ptr(self.variance),
+                                  ptr(self.lengthscales), ptr(self.gd), ptr(self.dW), ptr(self.dvar), ptr(self.dls),
+                                  ptr(self.ws), self.ws_bytes, st))
 
     def backward(self):
         L, s, st = _lib.lib(), self.spec, stream_ptr()
@@ -55,9 +79,7 @@ class HotPath:
         check(L.cgp_kuf_bwd(s.ref(), self.N, self.M, ptr(self.X), ptr(self.Z), ptr(self.W), ptr(self.variance),
                             ptr(self.lengthscales), ptr(self.G), ptr(self.dZ), ptr(self.dW), ptr(self.dvar),
                             ptr(self.dls), ptr(self.ws), self.ws_bytes, st))
-        check(L.cgp_kdiag_bwd(s.ref(), self.N, ptr(self.X), ptr(self.W), ptr(self.variance), ptr(self.lengthscales),
-                              ptr(self.gd), ptr(self.dW), ptr(self.dvar), ptr(self.dls), ptr(self.ws),
-                              self.ws_bytes, st))
+        self._kdiag_bwd(st)
         check(L.cgp_kuu_bwd(s.ref(), self.M, ptr(self.Z), ptr(self.variance), ptr(self.lengthscales), ptr(self.Gu),
                             ptr(self.dZ), ptr(self.dvar), ptr(self.dls), st))
 
@@ -79,17 +101,14 @@ class HotPath:
         # forward
         check(L.cgp_kuf_fwd(s.ref(), self.N, self.M, ptr(self.X), ptr(self.Z), ptr(self.W), ptr(self.variance),
                             ptr(self.lengthscales), ptr(self.Kuf), ptr(self.ws), self.ws_bytes, sp(main)))
-        check(L.cgp_kdiag_fwd(s.ref(), self.N, ptr(self.X), ptr(self.W), ptr(self.variance), ptr(self.lengthscales),
-                              ptr(self.Kdiag), ptr(self.ws), self.ws_bytes, sp(s1)))
+        self._kdiag_fwd(sp(s1))
         check(L.cgp_kuu_fwd(s.ref(), self.M, ptr(self.Z), ptr(self.variance), ptr(self.lengthscales), self.diag_add,
                             ptr(self.Kuu), sp(s2)))
         # backward (all three accumulate atomically into the packed gradient buffer)
         check(L.cgp_kuf_bwd(s.ref(), self.N, self.M, ptr(self.X), ptr(self.Z), ptr(self.W), ptr(self.variance),
                             ptr(self.lengthscales), ptr(self.G), ptr(self.dZ), ptr(self.dW), ptr(self.dvar),
                             ptr(self.dls), ptr(self.ws), self.ws_bytes, sp(main)))
-        check(L.cgp_kdiag_bwd(s.ref(), self.N, ptr(self.X), ptr(self.W), ptr(self.variance), ptr(self.lengthscales),
-                              ptr(self.gd), ptr(self.dW), ptr(self.dvar), ptr(self.dls), ptr(self.ws),
-                              self.ws_bytes, sp(s1)))
+        self._kdiag_bwd(sp(s1))
         check(L.cgp_kuu_bwd(s.ref(), self.M, ptr(self.Z), ptr(self.variance), ptr(self.lengthscales), ptr(self.Gu),
                             ptr(self.dZ), ptr(self.dvar), ptr(self.dls), sp(s2)))
         for st in (s1, s2):

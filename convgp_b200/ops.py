@@ -55,31 +55,50 @@ class _Kuf(torch.autograd.Function):
 
 
 class _Kdiag(torch.autograd.Function):
+    """Kdiag and its gradients.  When a gradient will be asked for and the configuration is covered
+    (``cgp_kdiag_saved_elems`` > 0), the forward is the one that also stores the per-image row sums its backward is
+    made of (N * (P + 2) elements) and the backward is an O(N P) kernel; otherwise the backward recomputes."""
+
     @staticmethod
     def forward(ctx, spec, X, W, variance, lengthscales):
+        needs_grad = any(ctx.needs_input_grad[2:5])
         X, W, variance, lengthscales = map(_c, (X, W, variance, lengthscales))
         N = X.shape[0]
         shape = (N, spec.C) if spec.per_channel else (N,)
         out = torch.empty(shape, dtype=X.dtype, device=X.device)
+        saved = None
         with torch.cuda.device(X.device):
-            ws, nb = spec.workspace(N, 0, X.device)
-            check(_lib.lib().cgp_kdiag_fwd(spec.ref(), N, ptr(X), ptr(W), ptr(variance), ptr(lengthscales), ptr(out),
-                                           ptr(ws), nb, stream_ptr()))
+            L = _lib.lib()
+            n_saved = L.cgp_kdiag_saved_elems(spec.ref(), N) if needs_grad and N > 0 else 0
+            if n_saved:
+                saved = torch.empty(n_saved, dtype=X.dtype, device=X.device)
+                check(L.cgp_kdiag_fwd_saved(spec.ref(), N, ptr(X), ptr(W), ptr(variance), ptr(lengthscales), ptr(out),
+                                            ptr(saved), n_saved, stream_ptr()))
+            else:
+                ws, nb = spec.workspace(N, 0, X.device)
+                check(L.cgp_kdiag_fwd(spec.ref(), N, ptr(X), ptr(W), ptr(variance), ptr(lengthscales), ptr(out),
+                                      ptr(ws), nb, stream_ptr()))
         ctx.spec = spec
-        ctx.save_for_backward(X, W, variance, lengthscales)
+        ctx.has_saved = saved is not None
+        ctx.save_for_backward(X, W, variance, lengthscales, saved)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        X, W, variance, lengthscales = ctx.saved_tensors
+        X, W, variance, lengthscales, saved = ctx.saved_tensors
         spec = ctx.spec
         N = X.shape[0]
         _, (_, dW, dvar, dls) = _grad_buffers(spec, None, W, variance, lengthscales)
         g = g.contiguous()
         with torch.cuda.device(X.device):
-            ws, nb = spec.workspace(N, 0, X.device)
-            check(_lib.lib().cgp_kdiag_bwd(spec.ref(), N, ptr(X), ptr(W), ptr(variance), ptr(lengthscales), ptr(g),
-                                           ptr(dW), ptr(dvar), ptr(dls), ptr(ws), nb, stream_ptr()))
+            if ctx.has_saved:
+                check(_lib.lib().cgp_kdiag_bwd_saved(spec.ref(), N, ptr(variance), ptr(lengthscales), ptr(g),
+                                                     ptr(saved), saved.numel(), ptr(dW), ptr(dvar), ptr(dls),
+                                                     stream_ptr()))
+            else:
+                ws, nb = spec.workspace(N, 0, X.device)
+                check(_lib.lib().cgp_kdiag_bwd(spec.ref(), N, ptr(X), ptr(W), ptr(variance), ptr(lengthscales),
+                                               ptr(g), ptr(dW), ptr(dvar), ptr(dls), ptr(ws), nb, stream_ptr()))
         return None, None, dW, dvar, dls
 
 

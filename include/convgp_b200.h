@@ -99,6 +99,19 @@ int cgp_kdiag_bwd(const cgp_kernel_desc* d, int32_t N, const void* X, const void
                   const void* lengthscales, const void* g, void* dW, void* dvariance, void* dlengthscales,
                   void* ws, size_t ws_bytes, void* stream);
 
+/* Kdiag forward that also stores what its backward is made of, and the O(N P) backward that consumes it
+ * (the reference gets this for free from TF autodiff, which keeps the P x P Gram of convkernels.py:173-181
+ * alive between the passes; here only N * (P + 2) elements are kept: per image the row sums
+ * r[n, q] = sum_q' w_q' k(x_nq, x_nq'), v[n] = sum_q w_q r[n, q] and v2[n] = sum w w k * arg).
+ * cgp_kdiag_saved_elems returns the element count of `saved` (caller-owned, dtype of the descriptor), or 0
+ * when the configuration is not covered -- then use cgp_kdiag_fwd / cgp_kdiag_bwd. */
+size_t cgp_kdiag_saved_elems(const cgp_kernel_desc* d, int32_t N);
+int cgp_kdiag_fwd_saved(const cgp_kernel_desc* d, int32_t N, const void* X, const void* W, const void* variance,
+                        const void* lengthscales, void* Kdiag, void* saved, size_t saved_elems, void* stream);
+int cgp_kdiag_bwd_saved(const cgp_kernel_desc* d, int32_t N, const void* variance, const void* lengthscales,
+                        const void* g, const void* saved, size_t saved_elems, void* dW, void* dvariance,
+                        void* dlengthscales, void* stream);
+
 /* Kzz (convkernels.py:89-90): basekern.K(Z); `diag_add` (jitter + White variance, svsumgp.py:76,
  * misvgp.py:196) is added to the diagonal in the same pass. */
 int cgp_kuu_fwd(const cgp_kernel_desc* d, int32_t M, const void* Z, const void* variance,
