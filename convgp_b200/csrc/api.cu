@@ -329,9 +329,10 @@ static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int
 // patches per CTA group, the (image, patch tile) units of the tile split evenly over the group.
 static int run_umma_dz(const cgp_kernel_desc* d, const Geo& g, int N, int M, const void* X, const void* Z,
                        const void* W, const void* var, const void* ls, const void* G, void* dZ, void* dvar,
-                       void* dls, cudaStream_t st) {
+                       void* dls, cudaStream_t st, void* dW = nullptr) {
   umma::Params p;
   memset(&p, 0, sizeof(p));
+  p.dW = (float*)dW;
   p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
   p.ls = (const float*)ls; p.G = (const float*)G; p.dZ = (float*)dZ; p.dvar = (float*)dvar; p.dls = (float*)dls;
   p.N = N; p.M = M; p.H = d->H; p.Wd = d->W; p.Hout = g.Hout; p.Wout = g.Wout; p.P = g.P; p.D = g.D;
@@ -395,11 +396,16 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
       if (!BWD) return run_umma_rowsum(0, d, g, N, M, X, Z, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st);
       // the backward kernel's two-deep ring of per-image arrays needs at least two patch tiles per image
       if (g.P > umma::TN) {
-      if (dZ || dvar || dls) {
-        int rc = run_umma_dz(d, g, N, M, X, Z, W, var, ls, G, dZ, dvar, dls, st);
+      // dW rides in the dZ kernel (column sums of the same exponentials); CGP_KUF_DW_PASS=1 selects the
+      // stand-alone pass (rowsum mode 3) instead
+      static const int dw_pass = env_choice("CGP_KUF_DW_PASS", 0);
+      const bool want_dw = dW && W;
+      if (dZ || dvar || dls || (want_dw && !dw_pass)) {
+        int rc = run_umma_dz(d, g, N, M, X, Z, W, var, ls, G, dZ, dvar, dls, st, (want_dw && !dw_pass) ? dW : nullptr);
         if (rc != CGP_OK) return rc;
       }
-      if (dW && W) return run_umma_rowsum(3, d, g, N, M, X, Z, W, var, ls, G, nullptr, dW, nullptr, nullptr, st);
+      if (want_dw && dw_pass)
+        return run_umma_rowsum(3, d, g, N, M, X, Z, W, var, ls, G, nullptr, dW, nullptr, nullptr, st);
       return CGP_OK;
       }
     }

@@ -399,7 +399,7 @@ constexpr int kIssuerWarp = kProd / 32, kEpiWarp0 = kProd / 32 + 1;
 
 // shared-memory plan (bytes), shared by host and device
 struct Smem {
-  int sB, wc, img, zbuf, w, racc, red, bars, total;
+  int sB, wc, img, zbuf, w, org, racc, red, bars, total;
 };
 __host__ __device__ inline Smem smem_plan(int KP, int HW, int P, int R) {  // R: longest row-accumulator array
   Smem s;
@@ -414,6 +414,8 @@ __host__ __device__ inline Smem smem_plan(int KP, int HW, int P, int R) {  // R:
   o += 2 * TM * (KP - 2) * 4;
   s.w = o;
   o += (P * 4 + 15) / 16 * 16;
+  s.org = o;  // patch index -> offset of its origin in the image (no integer division in the unit loop: the
+  o += (P * 4 + 15) / 16 * 16;  // divide's I2F / MUFU.RCP / F2I queue behind the epilogue's ex2 on the XU pipe)
   s.racc = o;  // row accumulators: [2 column halves][2 (sum k, sum k S)][P]
   o += 4 * ((R * 4 + 15) / 16 * 16);
   s.red = o;
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
   const int pre_stride = 4 * img_stride + 2 * p_stride;
   float* zbuf = reinterpret_cast<float*>(smem + L.zbuf);
   float* w = reinterpret_cast<float*>(smem + L.w);
+  int* org = reinterpret_cast<int*>(smem + L.org);
   float* racc = reinterpret_cast<float*>(smem + L.racc);
   const int Pp = (Racc * 4 + 15) / 16 * 4;  // padded accumulator length (floats)
   float* red = reinterpret_cast<float*>(smem + L.red);
@@ -478,7 +481,10 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
     p.trace[63 * 24 + (blockIdx.x ? 5 : 1)] = clock64();
   }
 #endif
-  for (int i = tid; i < p.P; i += kThreads) w[i] = p.Wt ? p.Wt[i] : 1.f;
+  for (int i = tid; i < p.P; i += kThreads) {
+    w[i] = p.Wt ? p.Wt[i] : 1.f;
+    org[i] = (i / p.Wout) * p.Wd + (i % p.Wout);
+  }
   for (int i = tid; i < 4 * Pp; i += kThreads) racc[i] = 0.f;
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
@@ -536,6 +542,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
     for (int u = 0; u < nun; ++u, it.next()) {
       const Unit un = decode(mode, it);
       if (pt == 0) CGP_TRACE(0, u);
+      if (pt == 32) CGP_TRACE(8, u);
       const bool needA = un.akey != akey, needB = un.bkey != bkey;
       // (with a single unit per image the rings are only safe once unit u-2 is fully staged by everyone)
       if (units_per_image < 2 && u >= 2) mbar_wait(&mma_done[u & 1], ((u >> 1) - 1) & 1);
@@ -557,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
           split_tf32(x * (2.f * c2), wsh[i], wsl[i]);
         }
         for (int q = pt; q < p.P; q += kProd) {
-          const float* base = raw + (q / p.Wout) * p.Wd + (q % p.Wout);
+          const float* base = raw + org[q];
           float ss = 0.f;
 #pragma unroll
           for (int i = 0; i < PH; ++i)
@@ -582,10 +589,14 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
           gather_row<PH, PW, KP>(x, g < p.M, true, 2.f * c2, c2, zbuf + ((u & 1) * TM + pt) * D, PW);
           split_row<KP>(x, ahi, alo);
         } else {
-          const int gg = min(g, p.P - 1), o = (gg / p.Wout) * p.Wd + (gg % p.Wout);
+          const int gg = min(g, p.P - 1), o = org[gg];
           load_patch_row<PH, PW, KP>(ahi, alo, g < p.P, true, sh + o, sl + o, p.Wd, eh[gg], el[gg]);
         }
       }
+#ifdef CGP_UMMA_TRACE
+      if (needA && pt < TM) asm volatile("" ::"f"(ahi[0]), "f"(ahi[24]), "f"(alo[24]), "f"(ahi[25]));  // loads landed
+      if (pt == 32) CGP_TRACE(12, u);
+#endif
       if (a_is_z && pt < TM && u + 1 < nun) {  // fetch the next unit's Z row (asynchronous, into shared memory)
         UnitIter nx = it;
         nx.next();
@@ -636,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
             gather_row<PH, PW, KP>(x, g < p.M, false, 1.f, c2, p.Z + (size_t)min(g, p.M - 1) * D, PW);
             split_row<KP>(x, xhi, xlo);
           } else {
-            const int gg = min(g, p.P - 1), o = (gg / p.Wout) * p.Wd + (gg % p.Wout);
+            const int gg = min(g, p.P - 1), o = org[gg];
             load_patch_row<PH, PW, KP>(xhi, xlo, g < p.P, false, xh + o, xl + o, p.Wd, eh[gg], el[gg]);
           }
           put_row_smem<KP>(buf, TN, r, xhi, xlo);
@@ -867,7 +878,8 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
 
 
 // =====================================================================================
-// Kuf backward, dZ / dvariance / dlengthscale part (dW comes from rowsum mode 3).
+// Kuf backward: dZ, dvariance, dlengthscale, and dW (column sums of the same exponentials across the tile's
+// rows; rowsum mode 3 is the stand-alone dW pass kept as a tested variant, CGP_KUF_DW_PASS=1).
 //
 // Flash-attention shaped: per unit (image n, tile of 192 patches) of one tile of 128 inducing rows
 //   GEMM1  S = Z . X^T            tf32 x3, A = Z tile (TMEM, resident), B = patches (shared memory)
@@ -881,7 +893,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
 constexpr int kDzProd = 224;  // warps 0-7 epilogue, 8-14 producers (7 warps), 15 issues the MMAs
 
 struct DzSmem {
-  int sB, sBt, wc, img, pre, pre_stride, org, w, red, part, bars, total;
+  int sB, sBt, wc, img, pre, pre_stride, org, w, red, part, dws, bars, total;
 };
 __host__ __device__ inline DzSmem dz_smem_plan(int KP, int HW, int P) {
   DzSmem s;
@@ -907,10 +919,28 @@ __host__ __device__ inline DzSmem dz_smem_plan(int KP, int HW, int P) {
   o += 64;
   s.part = o;
   o += 2 * TM * 4;
+  s.dws = o;  // dW accumulators of the CTA: one per patch column of every patch tile
+  o += (P + TN - 1) / TN * TN * 4;
   s.bars = o;
   o += 160;
   s.total = o;
   return s;
+}
+
+// Column sums over the 32 lanes of a warp for 32 per-lane values ("transpose-reduce"): after five
+// exchange-and-halve steps lane L holds sum over lanes of x[L].  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_column_sums(float (&x)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? x[i] : x[i + h];
+      const float keep = up ? x[i + h] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return x[0];
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float odd_k, float even_k) {  // even k in the low half
@@ -940,6 +970,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
   float* w = reinterpret_cast<float*>(smem + L.w);
   float* red = reinterpret_cast<float*>(smem + L.red);
   float* part = reinterpret_cast<float*>(smem + L.part);
+  float* dws = reinterpret_cast<float*>(smem + L.dws);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* staged = bars;          // [2] producers -> issuer: GEMM1's B operand of the unit is in shared memory
   uint64_t* g1_done = bars + 2;     // [2] GEMM1 of the unit complete (S readable, its B slot reusable)
@@ -963,6 +994,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
     w[i] = p.Wt ? p.Wt[i] : 1.f;
     org[i] = (i / p.Wout) * p.Wd + (i % p.Wout);
   }
+  for (int i = tid; i < p.E2 * TN; i += kNT) dws[i] = 0.f;
   // the transposed bf16 operand keeps zero rows for the padded dims d >= D: clear it once
   for (int i = tid; i < (int)(3 * BT_SLOT / 4); i += kNT) reinterpret_cast<uint32_t*>(sBt)[i] = 0u;
   if (tid == 0) {
@@ -1216,9 +1248,11 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
     float s0 = 0.f, s2 = 0.f;  // sum coef, sum coef * S over this thread's columns
     const float invP = 1.f / p.Pn;
     float gnext = 0.f;
+    const bool do_dw = p.dW != nullptr;
     if (nun > 0 && mval) gnext = p.G[(size_t)m * p.N + (int)(lo / n_pt)];
     for (int u = 0; u < nun; ++u) {
       const float Gm = gnext * invP;
+      float* dwu = dws + (int)((lo + u) % n_pt) * TN + half * 96 + lane;  // this lane's column of each chunk
       if (u + 1 < nun && mval) gnext = p.G[(size_t)m * p.N + (int)((lo + u + 1) / n_pt)];
       if (et == 0) CGP_TRACE(5, u);
       mbar_wait(&g1_done[u & 1], (u >> 1) & 1);
@@ -1241,9 +1275,11 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float s = __uint_as_float(v[4 * q + i]);
-            cf[i] = Gm * ww[i] * ex2f(s);
+            const float c0 = Gm * ex2f(s);  // G[m, n] / P * k: dW's summand, before the patch weight
+            cf[i] = c0 * ww[i];
             s0 += cf[i];
             s2 = fmaf(cf[i], s, s2);
+            v[4 * q + i] = __float_as_uint(c0);
           }
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
@@ -1257,6 +1293,14 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
         // c1 of this chunk goes to packed columns 16 c .. 16 c + 15 of the half: already consumed
         tmem_st8(tbuf + 16 * c, c1p);
         tmem_st8(tbuf + 16 * c + 8, c1p + 8);
+        if (do_dw) {
+          // dW[p] = sigma^2 sum_{m, n} G[m, n] / P * k[m, n, p]: the sum over the tile's 128 rows is a column
+          // sum across lanes (and the four lane quarters); lane L ends up with column 32 c + L of this half
+          float cs[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) cs[i] = __uint_as_float(v[i]);
+          atomicAdd(dwu + 32 * c, warp_column_sums(cs, lane));
+        }
       }
 #pragma unroll
       for (int k = 0; k < 6; ++k) tmem_st8(tbuf + 48 + 8 * k, c2hold + 8 * k);
@@ -1275,6 +1319,11 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
       part[row] = s0;
     }
     named_sync(2, kEpi);
+    if (do_dw)
+      for (int i = et; i < p.P; i += kEpi) {
+        const float v = dws[i];
+        if (v != 0.f) atomicAdd(p.dW + i, sig2 * v);
+      }
     const float s0row = half == 0 ? s0 + part[row] : 0.f;
     if (half == 0 && nun > 0 && p.dZ) {  // warp-uniform: tcgen05.ld is a warp-collective
       uint32_t d1[32], dd2[32];
