@@ -69,7 +69,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, A/B format, K-major both.
-constexpr uint32_t kFmtTF32 = 2, kFmtBF16 = 1;
+constexpr uint32_t kFmtTF32 = 2, kFmtBF16 = 1, kFmtF16 = 0;
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -883,10 +883,11 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
 //
 // Flash-attention shaped: per unit (image n, tile of 192 patches) of one tile of 128 inducing rows
 //   GEMM1  S = Z . X^T            tf32 x3, A = Z tile (TMEM, resident), B = patches (shared memory)
-//   epilogue  coef = G[m,n]/P * w_p * ex2(S)   -> two bf16 terms c1 + c2, written back over S in TMEM
-//   GEMM2  dz += coef . X         kind::f16 (bf16), A = c1 / c2 from TMEM, B = X^T as bf16 terms x1 | x2
-//          (c1.x1 + c1.x2 + c2.x1: <= 1e-5 relative, a single bf16 or tf32 coefficient is not enough
-//           because dZ = sum coef (x - z) cancels; the sums use the same rounded coefficients)
+//   epilogue  coef = G[m,n]/P * w_p * ex2(S)   -> ONE fp16 term (scaled by a CTA-uniform power of two), written
+//             back over S in TMEM
+//   GEMM2  dz += coef . [X | 1]   kind::f16, A = coef from TMEM, B = X^T as two fp16 terms x1 | x2 plus a row of
+//          ones: column D of dz is sum_p coef from the SAME rounded coefficients, so dZ = sum coef (x - z) -- which
+//          cancels heavily -- sees only the relative rounding of each term (2^-12), not the cancellation
 // and at the end dZ = sigma^2 / l^2 (dz - z * sum coef).  A CTA owns one row tile for its whole life,
 // so the dz accumulator (64 TMEM columns) is read exactly once.  TMEM: S0 | S1 | dz | Z = 512 columns.
 // =====================================================================================
@@ -943,6 +944,21 @@ __device__ __forceinline__ float warp_column_sums(float (&x)[32], int lane) {
   return x[0];
 }
 
+__device__ __forceinline__ uint32_t pack_f16x2(float odd_k, float even_k) {  // even k in the low half
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd_k), "f"(even_k));
+  return r;
+}
+__device__ __forceinline__ float f16_lo_to_f32(uint32_t packed) {
+  float f;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}\n" : "=f"(f) : "r"(packed));
+  return f;
+}
+__device__ __forceinline__ float f16_hi_to_f32(uint32_t packed) {
+  float f;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}\n" : "=f"(f) : "r"(packed));
+  return f;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float odd_k, float even_k) {  // even k in the low half
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd_k), "f"(even_k));
@@ -996,7 +1012,12 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
   }
   for (int i = tid; i < p.E2 * TN; i += kNT) dws[i] = 0.f;
   // the transposed bf16 operand keeps zero rows for the padded dims d >= D: clear it once
-  for (int i = tid; i < (int)(3 * BT_SLOT / 4); i += kNT) reinterpret_cast<uint32_t*>(sBt)[i] = 0u;
+  // ... except row D of the x1 part, which is all ones: GEMM2 then also accumulates sum_p coef[m, p] (column D of
+  // dz) from the SAME rounded coefficients the dz columns use, so dz - z * sum coef cancels consistently
+  for (int i = tid; i < (int)(3 * BT_SLOT / 4); i += kNT) {
+    const int r = (4 * i) % 1024;  // byte inside the 64-row x 16-byte block of one patch octet
+    reinterpret_cast<uint32_t*>(sBt)[i] = (r / 128 == (D >> 3) && (r % 128) / 16 == (D & 7)) ? 0x3C003C00u : 0u;
+  }
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&staged[b], kDzProd / 32);
@@ -1082,16 +1103,15 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
 #pragma unroll
           for (int e2 = 0; e2 < 3; ++e2) {
             x[e2] = 2 * i + e2 < HW ? raw[2 * i + e2] : 0.f;
-            const uint32_t t1 = pack_bf16x2(0.f, x[e2]);
-            b1[e2] = __uint_as_float(t1 << 16);
+            b1[e2] = f16_lo_to_f32(pack_f16x2(0.f, x[e2]));
             b2[e2] = x[e2] - b1[e2];
           }
           split_tf32(x[0], wxh[2 * i], wxl[2 * i]);
           if (2 * i + 1 < HW) split_tf32(x[1], wxh[2 * i + 1], wxl[2 * i + 1]);
-          w1e[i] = pack_bf16x2(b1[1], b1[0]);
-          w1o[i] = pack_bf16x2(b1[2], b1[1]);
-          w2e[i] = pack_bf16x2(b2[1], b2[0]);
-          w2o[i] = pack_bf16x2(b2[2], b2[1]);
+          w1e[i] = pack_f16x2(b1[1], b1[0]);
+          w1o[i] = pack_f16x2(b1[2], b1[1]);
+          w2e[i] = pack_f16x2(b2[1], b2[0]);
+          w2o[i] = pack_f16x2(b2[2], b2[1]);
         }
         for (int q = pt; q < p.P; q += kDzProd) {
           const float* base = raw + org[q];
@@ -1150,9 +1170,9 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
                   const int g = g0 + 2 * h + e2;
                   xv[e2] = g < p.P ? raw[org[g] + doff] : 0.f;
                 }
-                const uint32_t a1 = pack_bf16x2(xv[1], xv[0]);
+                const uint32_t a1 = pack_f16x2(xv[1], xv[0]);
                 q1[it2][h] = a1;
-                q2[it2][h] = pack_bf16x2(xv[1] - __uint_as_float(a1 & 0xFFFF0000u), xv[0] - __uint_as_float(a1 << 16));
+                q2[it2][h] = pack_f16x2(xv[1] - f16_hi_to_f32(a1), xv[0] - f16_lo_to_f32(a1));
               }
             }
           }
@@ -1192,7 +1212,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
     // ============================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t id1 = make_idesc(TM, TN, kFmtTF32);
-      constexpr uint32_t id2a = make_idesc(TM, 64, kFmtBF16), id2b = make_idesc(TM, 32, kFmtBF16);
+      constexpr uint32_t id2a = make_idesc(TM, 64, kFmtF16);
       const uint64_t dbh0 = make_desc(smem_u32(sB), 16 * TN, 128);
       const uint64_t dbt0 = make_desc(smem_u32(sBt), 16 * 64, 128);
       const uint32_t ah = tmem_base + kTmemA, al = ah + KP, d2 = tmem_base + kTmemD2;
@@ -1208,8 +1228,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
 #pragma unroll
           for (int t = 0; t < 6; ++t) {
             const uint64_t db = dbt + (uint64_t)(((h * 96 + t * 16) / 8) * ((16 * 64) >> 4));
-            mma_bf16_ts(d2, sc + h * 96 + 8 * t, db, id2a, (u | h | t) != 0);  // c1 . [x1 | x2]
-            mma_bf16_ts(d2, sc + h * 96 + 48 + 8 * t, db, id2b, 1);            // c2 . x1
+            mma_bf16_ts(d2, sc + h * 96 + 8 * t, db, id2a, (u | h | t) != 0);  // coef . [x1 | x2]
           }
         mma_commit(&g2_done[u % 3]);
         CGP_TRACE(13, u);
@@ -1245,13 +1264,47 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int m = m0 + row;
     const bool mval = m < p.M;
-    float s0 = 0.f, s2 = 0.f;  // sum coef, sum coef * S over this thread's columns
+    float s2 = 0.f;  // sum coef * S over this thread's columns
     const float invP = 1.f / p.Pn;
+    // The coefficients go to the tensor core as ONE fp16 term (11 significant bits; fp16 needs a scale: a power of
+    // two, uniform over the CTA so that the dW column sums across rows stay meaningful, chosen so that the largest
+    // possible |coef| = max|G| max|w| / P lands at 2^14; everything is unscaled once at the end).
+    float cscale = 1.f, inv_cscale = 1.f;
+    {
+      float gm = 0.f, wm = 0.f;
+      if (mval && nun > 0)
+        for (int n = (int)(lo / n_pt) + half; n <= (int)((hi - 1) / n_pt); n += 2)
+          gm = fmaxf(gm, fabsf(p.G[(size_t)m * p.N + n]));
+      for (int i = et; i < p.P; i += kEpi) wm = fmaxf(wm, fabsf(w[i]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+        wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+      }
+      if (lane == 0) {
+        red[ew] = gm;
+        red[8 + ew] = wm;
+      }
+      named_sync(2, kEpi);
+      gm = wm = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        gm = fmaxf(gm, red[k]);
+        wm = fmaxf(wm, red[8 + k]);
+      }
+      named_sync(2, kEpi);
+      const float t = gm * invP * wm;
+      if (t > 0.f && t < 3.0e38f) {
+        int e = min(max(14 - (ilogbf(t) + 1), -100), 100);
+        cscale = exp2f((float)e);
+        inv_cscale = exp2f((float)-e);
+      }
+    }
     float gnext = 0.f;
     const bool do_dw = p.dW != nullptr;
     if (nun > 0 && mval) gnext = p.G[(size_t)m * p.N + (int)(lo / n_pt)];
     for (int u = 0; u < nun; ++u) {
-      const float Gm = gnext * invP;
+      const float Gm = gnext * invP * cscale;
       float* dwu = dws + (int)((lo + u) % n_pt) * TN + half * 96 + lane;  // this lane's column of each chunk
       if (u + 1 < nun && mval) gnext = p.G[(size_t)m * p.N + (int)((lo + u + 1) / n_pt)];
       if (et == 0) CGP_TRACE(5, u);
@@ -1260,7 +1313,6 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
       tc_fence_after();
       const uint32_t tbuf = lane_addr + (uint32_t)(u & 1) * TN + (uint32_t)half * 96;
       const float4* wc4 = reinterpret_cast<const float4*>(wc + (u & 3) * TN + half * 96);
-      uint32_t c2hold[48];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         uint32_t v[32];
@@ -1277,18 +1329,11 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
             const float s = __uint_as_float(v[4 * q + i]);
             const float c0 = Gm * ex2f(s);  // G[m, n] / P * k: dW's summand, before the patch weight
             cf[i] = c0 * ww[i];
-            s0 += cf[i];
             s2 = fmaf(cf[i], s, s2);
             v[4 * q + i] = __float_as_uint(c0);
           }
-#pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const uint32_t a1 = pack_bf16x2(cf[2 * h2 + 1], cf[2 * h2]);
-            const float f0 = __uint_as_float(a1 << 16), f1 = __uint_as_float(a1 & 0xFFFF0000u);
-            const uint32_t a2 = pack_bf16x2(cf[2 * h2 + 1] - f1, cf[2 * h2] - f0);
-            c1p[2 * q + h2] = a1;
-            c2hold[16 * c + 2 * q + h2] = a2;
-          }
+          c1p[2 * q] = pack_f16x2(cf[1], cf[0]);
+          c1p[2 * q + 1] = pack_f16x2(cf[3], cf[2]);
         }
         // c1 of this chunk goes to packed columns 16 c .. 16 c + 15 of the half: already consumed
         tmem_st8(tbuf + 16 * c, c1p);
@@ -1302,8 +1347,6 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
           atomicAdd(dwu + 32 * c, warp_column_sums(cs, lane));
         }
       }
-#pragma unroll
-      for (int k = 0; k < 6; ++k) tmem_st8(tbuf + 48 + 8 * k, c2hold + 8 * k);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -1315,34 +1358,34 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
       mbar_wait(&g2_done[(nun - 1) % 3], ((nun - 1) / 3) & 1);
       tc_fence_after();
     }
-    if (half == 1) {
-      part[row] = s0;
-    }
     named_sync(2, kEpi);
     if (do_dw)
       for (int i = et; i < p.P; i += kEpi) {
         const float v = dws[i];
-        if (v != 0.f) atomicAdd(p.dW + i, sig2 * v);
+        if (v != 0.f) atomicAdd(p.dW + i, sig2 * inv_cscale * v);
       }
-    const float s0row = half == 0 ? s0 + part[row] : 0.f;
-    if (half == 0 && nun > 0 && p.dZ) {  // warp-uniform: tcgen05.ld is a warp-collective
+    float s0row = 0.f;  // sum_p coef[m, p]: column D of the dz accumulator (the ones row of the transposed operand)
+    if (half == 0 && nun > 0) {  // warp-uniform: tcgen05.ld is a warp-collective
       uint32_t d1[32], dd2[32];
       tmem_ld32(lane_addr + kTmemD2, d1);
       tmem_ld32(lane_addr + kTmemD2 + 32, dd2);
       tmem_wait_ld(d1);
       tmem_wait_ld(dd2);
       if (mval) {
-        const float sc = sig2 / (lsv * lsv);
-        const float* zr = p.Z + (size_t)m * D;
+        s0row = __uint_as_float(d1[D]) * inv_cscale;
+        if (p.dZ) {
+          const float sc = sig2 / (lsv * lsv);
+          const float* zr = p.Z + (size_t)m * D;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          const float dz = __uint_as_float(d1[d]) + __uint_as_float(dd2[d]);
-          atomicAdd(p.dZ + (size_t)m * D + d, sc * (dz - zr[d] * s0row));
+          for (int d = 0; d < D; ++d) {
+            const float dz = (__uint_as_float(d1[d]) + __uint_as_float(dd2[d])) * inv_cscale;
+            atomicAdd(p.dZ + (size_t)m * D + d, sc * (dz - zr[d] * s0row));
+          }
         }
       }
     }
     {
-      float t0 = warp_sum(mval ? s0 : 0.f), t2 = warp_sum(mval ? s2 : 0.f);
+      float t0 = warp_sum(s0row), t2 = warp_sum(mval ? s2 * inv_cscale : 0.f);
       named_sync(2, kEpi);
       if (lane == 0) {
         red[ew] = t0;
