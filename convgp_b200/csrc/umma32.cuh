@@ -276,11 +276,12 @@ __device__ __forceinline__ void gather_row(float (&x)[KP], bool valid, bool scal
   }
 }
 
-// Patch row from the pre-split image arrays (vh/vl point at the patch origin): slot values are pure
-// loads -- the hi/lo split and the squared norm were done once per image, not once per patch element.
+// Patch row from the pre-split image array (v points at the patch origin; element = (hi, lo) of one pixel, so one
+// 64-bit shared-memory load fetches both TF32 terms): slot values are pure loads -- the hi/lo split and the squared
+// norm were done once per image, not once per patch element.
 template <int PH, int PW, int KP>
 __device__ __forceinline__ void load_patch_row(float (&hi)[KP], float (&lo)[KP], bool valid, bool scaled,
-                                               const float* vh, const float* vl, int stride, float eh, float el) {
+                                               const float2* v, int stride, float2 e) {
   constexpr int D = PH * PW;
 #pragma unroll
   for (int d = 0; d < KP; ++d) hi[d] = lo[d] = 0.f;
@@ -289,13 +290,14 @@ __device__ __forceinline__ void load_patch_row(float (&hi)[KP], float (&lo)[KP],
     for (int i = 0; i < PH; ++i)
 #pragma unroll
       for (int j = 0; j < PW; ++j) {
-        hi[i * PW + j] = vh[i * stride + j];
-        lo[i * PW + j] = vl[i * stride + j];
+        const float2 t = v[i * stride + j];
+        hi[i * PW + j] = t.x;
+        lo[i * PW + j] = t.y;
       }
-    hi[D] = scaled ? eh : 1.f;
-    lo[D] = scaled ? el : 0.f;
-    hi[D + 1] = scaled ? 1.f : eh;
-    lo[D + 1] = scaled ? 0.f : el;
+    hi[D] = scaled ? e.x : 1.f;
+    lo[D] = scaled ? e.y : 0.f;
+    hi[D + 1] = scaled ? 1.f : e.x;
+    lo[D + 1] = scaled ? 0.f : e.y;
   }
 }
 template <int KP>
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
       for (int i = pt; i < HW; i += kProd) cp_async4(dst + i, src + i);
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&img_bar[k % 3])) : "memory");
     };
-    const float *xh = nullptr, *xl = nullptr, *sh = nullptr, *sl = nullptr, *eh = nullptr, *el = nullptr;
+    const float2 *xhl = nullptr, *shl = nullptr, *ehl = nullptr;  // (hi, lo) pairs: pixels, scaled pixels, norms
     const int units_per_image = mode == 3 ? p.E2 : p.E1 * p.E2;
     UnitIter it;
     it.init(lo, p.E1, p.E2);
@@ -555,13 +557,16 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
         fetch_image(nx < p.N ? nx : un.n, ki + 1);
         mbar_wait(&img_bar[ki % 3], (ki / 3) & 1);
         const float* raw = img0 + (ki % 3) * img_stride;
-        float* wxh = pre0 + (ki % 3) * pre_stride;
-        float *wxl = wxh + img_stride, *wsh = wxl + img_stride, *wsl = wsh + img_stride;
-        float *weh = wsl + img_stride, *wel = weh + p_stride;
+        float2* wx = reinterpret_cast<float2*>(pre0 + (ki % 3) * pre_stride);
+        float2* ws = wx + img_stride;  // img_stride float2 = 2 img_stride floats
+        float2* we = ws + img_stride;
         for (int i = pt; i < HW; i += kProd) {
           const float x = raw[i];
-          split_tf32(x, wxh[i], wxl[i]);
-          split_tf32(x * (2.f * c2), wsh[i], wsl[i]);
+          float2 a, b;
+          split_tf32(x, a.x, a.y);
+          split_tf32(x * (2.f * c2), b.x, b.y);
+          wx[i] = a;
+          ws[i] = b;
         }
         for (int q = pt; q < p.P; q += kProd) {
           const float* base = raw + org[q];
@@ -570,11 +575,13 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
           for (int i = 0; i < PH; ++i)
 #pragma unroll
             for (int j = 0; j < PW; ++j) ss = fmaf(base[i * p.Wd + j], base[i * p.Wd + j], ss);
-          split_tf32(-c2 * ss, weh[q], wel[q]);
+          float2 t;
+          split_tf32(-c2 * ss, t.x, t.y);
+          we[q] = t;
         }
         mbar_arrive(&pre_bar[ki % 3]);
         mbar_wait(&pre_bar[ki % 3], (ki / 3) & 1);
-        xh = wxh; xl = wxl; sh = wsh; sl = wsl; eh = weh; el = wel;
+        xhl = wx; shl = ws; ehl = we;
       }
       // The A row (registers) and the column weights are prepared BEFORE waiting for the operand
       // slots: only the TMEM / shared-memory stores sit in the MMA(u-2) -> stage -> MMA(u) loop.  Rows of
@@ -590,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
           split_row<KP>(x, ahi, alo);
         } else {
           const int gg = min(g, p.P - 1), o = org[gg];
-          load_patch_row<PH, PW, KP>(ahi, alo, g < p.P, true, sh + o, sl + o, p.Wd, eh[gg], el[gg]);
+          load_patch_row<PH, PW, KP>(ahi, alo, g < p.P, true, shl + o, p.Wd, ehl[gg]);
         }
       }
 #ifdef CGP_UMMA_TRACE
@@ -648,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
             split_row<KP>(x, xhi, xlo);
           } else {
             const int gg = min(g, p.P - 1), o = org[gg];
-            load_patch_row<PH, PW, KP>(xhi, xlo, g < p.P, false, xh + o, xl + o, p.Wd, eh[gg], el[gg]);
+            load_patch_row<PH, PW, KP>(xhi, xlo, g < p.P, false, xhl + o, p.Wd, ehl[gg]);
           }
           put_row_smem<KP>(buf, TN, r, xhi, xlo);
         }
@@ -1077,7 +1084,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
     // derived arrays of the current image (ring slot ki & 1)
     const int hw_al = (HW * 4 + 15) / 16 * 4, pk_al = ((HW / 2 + 2) * 4 + 15) / 16 * 4, p_al = (p.P * 4 + 15) / 16 * 4;
     unsigned char* pre0 = smem + L.pre;
-    const float *xh = nullptr, *xl = nullptr, *eh = nullptr, *el = nullptr;
+    const float2 *xhl = nullptr, *ehl = nullptr;  // (hi, lo) pairs of the pixels / patch norms
     const uint32_t *pk1e = nullptr, *pk1o = nullptr, *pk2e = nullptr, *pk2o = nullptr;
     for (int u = 0; u < nun; ++u) {
       const long long v = lo + u;
@@ -1106,8 +1113,16 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
             b1[e2] = f16_lo_to_f32(pack_f16x2(0.f, x[e2]));
             b2[e2] = x[e2] - b1[e2];
           }
-          split_tf32(x[0], wxh[2 * i], wxl[2 * i]);
-          if (2 * i + 1 < HW) split_tf32(x[1], wxh[2 * i + 1], wxl[2 * i + 1]);
+          {
+            float2* wx = reinterpret_cast<float2*>(wxh);  // spans the wxh and wxl regions
+            float2 t;
+            split_tf32(x[0], t.x, t.y);
+            wx[2 * i] = t;
+            if (2 * i + 1 < HW) {
+              split_tf32(x[1], t.x, t.y);
+              wx[2 * i + 1] = t;
+            }
+          }
           w1e[i] = pack_f16x2(b1[1], b1[0]);
           w1o[i] = pack_f16x2(b1[2], b1[1]);
           w2e[i] = pack_f16x2(b2[1], b2[0]);
@@ -1120,11 +1135,14 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
           for (int i = 0; i < PH; ++i)
 #pragma unroll
             for (int jj = 0; jj < PW; ++jj) ss = fmaf(base[i * p.Wd + jj], base[i * p.Wd + jj], ss);
-          split_tf32(-c2 * ss, weh[q], wel[q]);
+          float2 t;
+          split_tf32(-c2 * ss, t.x, t.y);
+          reinterpret_cast<float2*>(weh)[q] = t;  // spans the weh and wel regions
         }
         mbar_arrive(&pre_bar[ki & 1]);
         mbar_wait(&pre_bar[ki & 1], (ki >> 1) & 1);
-        xh = wxh; xl = wxl; pk1e = w1e; pk1o = w1o; pk2e = w2e; pk2o = w2o; eh = weh; el = wel;
+        xhl = reinterpret_cast<const float2*>(wxh); pk1e = w1e; pk1o = w1o; pk2e = w2e; pk2o = w2o;
+        ehl = reinterpret_cast<const float2*>(weh);
       }
       const float* raw = img0 + (ki % 3) * img_stride;
       if (pt == 64) CGP_TRACE(8, u);
@@ -1134,7 +1152,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
       float bhi[KP], blo[KP];
       if (r >= 0) {
         const int g = brow + r, gg = min(g, p.P - 1), o = org[gg];
-        load_patch_row<PH, PW, KP>(bhi, blo, g < p.P, false, xh + o, xl + o, p.Wd, eh[gg], el[gg]);
+        load_patch_row<PH, PW, KP>(bhi, blo, g < p.P, false, xhl + o, p.Wd, ehl[gg]);
       }
       if (pt < TN) {
         const int col = brow + pt;

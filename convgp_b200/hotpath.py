@@ -41,8 +41,8 @@ class HotPath:
         n_saved = _lib.lib().cgp_kdiag_saved_elems(spec.ref(), N) if N > 0 else 0
         self.kd_saved = torch.empty(n_saved, dtype=dt, device=dev) if n_saved else None
         self.graph = None
-        # Kuf / Kdiag / Kuu forward + backward; the float32 Kuf backward is two kernels (dZ part + dW pass)
-        self.kernels_per_step = 7 if dt == torch.float32 else 6
+        # Kuf / Kdiag / Kuu forward + backward: one kernel each
+        self.kernels_per_step = 6
 
     def forward(self):
         L, s, st = _lib.lib(), self.spec, stream_ptr()
