@@ -443,6 +443,12 @@ def run_gpu(args):
     sfl, sex = work["step"]
     ms_per_step = total_ms / args.steps
     step_frac = (t_bound(sfl, sex) if args.dtype == "f64" else step_bound) / (ms_per_step * 1e-3)
+    # The Kdiag backward consumes row sums its forward saved, so the library EXECUTES one sweep of the P x P Gram
+    # per step, not the two that SURVEY.md 8d's algorithmic count assumes: the same fraction on the executed work
+    # (the forward's 2D+2 flops + 1 exp per Kdiag pair taken out) is reported next to it.
+    kfl, kex = work["kdiag_fwd"]
+    step_frac_executed = ((t_bound(sfl - kfl, sex - kex) if args.dtype == "f64" else step_bound - t_bound(kfl, kex))
+                          / (ms_per_step * 1e-3)) if hp.kd_saved is not None else step_frac
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -450,7 +456,12 @@ def run_gpu(args):
         pass
     traffic = None
     try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.dtype, {}).get(dom)
+        for name in ("r1z_traffic.json", "r1_traffic.json"):  # latest capture first
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                traffic = json.load(open(path)).get(args.dtype, {}).get(dom)
+                if traffic is not None:
+                    break
     except Exception:
         pass
     images = N_BATCH * world
@@ -471,7 +482,7 @@ def run_gpu(args):
         "roofline": {
             "bound": pipe, "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_note,
-            "kernel_ms": per_kernel, "step_frac": step_frac,
+            "kernel_ms": per_kernel, "step_frac": step_frac, "step_frac_executed_work": step_frac_executed,
             "probes": peaks,
             "hbm": {"algorithmic_bytes_per_step": algorithmic_bytes(N_BATCH, es),
                     "achieved_gbs": algorithmic_bytes(N_BATCH, es) / (ms_per_step * 1e-3) / 1e9,

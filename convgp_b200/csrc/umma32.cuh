@@ -1012,6 +1012,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
   const long long lo = tot * share / per_tile, hi = tot * (share + 1) / per_tile;
   const int nun = (int)(hi - lo);
   const int m0 = mtile * TM;
+  const int n_first = (int)(lo / n_pt), j_first = (int)(lo % n_pt);  // unit coordinates are counted from here on
 
   for (int i = tid; i < p.P; i += kNT) {
     w[i] = p.Wt ? p.Wt[i] : 1.f;
@@ -1080,15 +1081,18 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
       for (int i = pt; i < HW; i += kDzProd) cp_async4(dst + i, src + i);
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&img_bar[k % 3])) : "memory");
     };
-    if (nun > 0) fetch_image((int)(lo / n_pt), 0);
+    if (nun > 0) fetch_image(n_first, 0);
+    int n = n_first, j = j_first - 1;
     // derived arrays of the current image (ring slot ki & 1)
     const int hw_al = (HW * 4 + 15) / 16 * 4, pk_al = ((HW / 2 + 2) * 4 + 15) / 16 * 4, p_al = (p.P * 4 + 15) / 16 * 4;
     unsigned char* pre0 = smem + L.pre;
     const float2 *xhl = nullptr, *ehl = nullptr;  // (hi, lo) pairs of the pixels / patch norms
     const uint32_t *pk1e = nullptr, *pk1o = nullptr, *pk2e = nullptr, *pk2o = nullptr;
     for (int u = 0; u < nun; ++u) {
-      const long long v = lo + u;
-      const int n = (int)(v / n_pt), j = (int)(v % n_pt);
+      if (++j == n_pt) {
+        j = 0;
+        ++n;
+      }
       if (pt == 0) CGP_TRACE(0, u);
       if (n != cur_img) {
         cur_img = n;
@@ -1291,7 +1295,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
     {
       float gm = 0.f, wm = 0.f;
       if (mval && nun > 0)
-        for (int n = (int)(lo / n_pt) + half; n <= (int)((hi - 1) / n_pt); n += 2)
+        for (int n = n_first + half; n <= (int)((hi - 1) / n_pt); n += 2)
           gm = fmaxf(gm, fabsf(p.G[(size_t)m * p.N + n]));
       for (int i = et; i < p.P; i += kEpi) wm = fmaxf(wm, fabsf(w[i]));
 #pragma unroll
@@ -1320,11 +1324,16 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
     }
     float gnext = 0.f;
     const bool do_dw = p.dW != nullptr;
-    if (nun > 0 && mval) gnext = p.G[(size_t)m * p.N + (int)(lo / n_pt)];
+    if (nun > 0 && mval) gnext = p.G[(size_t)m * p.N + n_first];
+    int n_cur = n_first, j_cur = j_first - 1;
     for (int u = 0; u < nun; ++u) {
       const float Gm = gnext * invP * cscale;
-      float* dwu = dws + (int)((lo + u) % n_pt) * TN + half * 96 + lane;  // this lane's column of each chunk
-      if (u + 1 < nun && mval) gnext = p.G[(size_t)m * p.N + (int)((lo + u + 1) / n_pt)];
+      if (++j_cur == n_pt) {
+        j_cur = 0;
+        ++n_cur;
+      }
+      float* dwu = dws + j_cur * TN + half * 96 + lane;  // this lane's column of each chunk
+      if (u + 1 < nun && mval) gnext = p.G[(size_t)m * p.N + (j_cur + 1 == n_pt ? n_cur + 1 : n_cur)];
       if (et == 0) CGP_TRACE(5, u);
       mbar_wait(&g1_done[u & 1], (u >> 1) & 1);
       if (et == 0) CGP_TRACE(6, u);

@@ -11,9 +11,12 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("family", ["umma", "mma", "fma"])
+@pytest.mark.parametrize("family", ["umma", "umma-dwpass", "mma", "fma"])
 def test_forced_kernel_family(family):
     env = dict(os.environ)
+    if family == "umma-dwpass":  # dW of Kuf from the stand-alone row-sum pass instead of the dZ kernel's column sums
+        env["CGP_KUF_DW_PASS"] = "1"
+        family = "umma"
     for k in ("CGP_KUF_FWD", "CGP_KUF_BWD", "CGP_KDIAG_FWD", "CGP_KDIAG_BWD"):
         env[k] = "mma" if family == "umma" else family  # float64 has no UMMA family (no FP64 tcgen05 kind)
         env[k + "_F32"] = family
