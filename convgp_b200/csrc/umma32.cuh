@@ -412,8 +412,8 @@ __host__ __device__ inline Smem smem_plan(int KP, int HW, int P, int R) {  // R:
   o += 8 * TN * 4;
   s.img = o;  // 3 raw buffers (cp.async ring), then a 3-deep ring of derived arrays: xh, xl, sh, sl (HW), eh, el (P)
   o += 3 * ((HW * 4 + 15) / 16 * 16) + 3 * (4 * ((HW * 4 + 15) / 16 * 16) + 2 * ((P * 4 + 15) / 16 * 16));
-  s.zbuf = o;  // two raw Z tiles (mode 0)
-  o += 2 * TM * (KP - 2) * 4;
+  s.zbuf = o;  // three raw Z tiles (mode 0): a cp.async ring, one mbarrier per buffer
+  o += 3 * TM * (KP - 2) * 4;
   s.w = o;
   o += (P * 4 + 15) / 16 * 16;
   s.org = o;  // patch index -> offset of its origin in the image (no integer division in the unit loop: the
@@ -430,6 +430,9 @@ __host__ __device__ inline Smem smem_plan(int KP, int HW, int P, int R) {  // R:
 
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -468,6 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
   uint64_t* img_bar = bars + 6;     // [3] image ring: every producer's cp.async of the buffer has landed
   uint64_t* pre_bar = bars + 9;     // [3] derived arrays of the image are complete
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* zbar = bars + 13;       // [3] Z-tile ring (mode 0): every producer's cp.async of the buffer has landed
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mode = p.mode;
@@ -497,6 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
     for (int b = 0; b < 3; ++b) {
       mbar_init(&img_bar[b], kProd);
       mbar_init(&pre_bar[b], kProd);
+      mbar_init(&zbar[b], kProd);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -532,15 +537,22 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
     const int units_per_image = mode == 3 ? p.E2 : p.E1 * p.E2;
     UnitIter it;
     it.init(lo, p.E1, p.E2);
-    // Z rows (mode 0: a new A tile every unit) are fetched one unit ahead with cp.async: no global-memory
-    // latency and no extra registers in a producer warp's per-unit critical path
-    auto fetch_zrow = [&](int g, int buf) {
-      const float* zr = p.Z + (size_t)min(g, p.M - 1) * D;
-      float* dst = zbuf + (buf * TM + pt) * D;
-#pragma unroll
-      for (int d = 0; d < D; ++d) cp_async4(dst + d, zr + d);
+    // Z tiles (mode 0: a new A tile every unit) are fetched one unit ahead with cp.async: no global-memory
+    // latency and no extra registers in a producer warp's per-unit critical path.  A tile is TM consecutive rows =
+    // one contiguous run of Z, so all producer threads copy it together in 16-byte pieces (coalesced; one row per
+    // thread in 4-byte pieces was 25 uncoalesced copies per thread and unit) into a three-deep ring, one mbarrier
+    // per buffer.  Tile k lives in buffer k % 3.
+    const bool z16 = (reinterpret_cast<uintptr_t>(p.Z) & 15) == 0;
+    auto fetch_ztile = [&](int arow, int k) {
+      const float* src = p.Z + (size_t)arow * D;
+      float* dst = zbuf + (k % 3) * TM * D;
+      const int nfl = max(0, min(TM, p.M - arow)) * D;  // floats of the tile that exist
+      const int n16 = z16 ? nfl / 4 : 0;
+      for (int i = pt; i < n16; i += kProd) cp_async16(dst + 4 * i, src + 4 * i);
+      for (int i = 4 * n16 + pt; i < nfl; i += kProd) cp_async4(dst + i, src + i);
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&zbar[k % 3])) : "memory");
     };
-    if (a_is_z && pt < TM && nun > 0) fetch_zrow(decode(mode, it).arow + pt, 0);
+    if (a_is_z && nun > 0) fetch_ztile(decode(mode, it).arow, 0);
     for (int u = 0; u < nun; ++u, it.next()) {
       const Unit un = decode(mode, it);
       if (pt == 0) CGP_TRACE(0, u);
@@ -591,9 +603,9 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
       if (needA && pt < TM) {  // warps 0-3: row pt -> TMEM lane pt
         const int g = un.arow + pt;
         if (a_is_z) {
-          cp_async_wait_all();  // this thread's own row, fetched one unit ago
+          mbar_wait(&zbar[u % 3], (u / 3) & 1);  // the tile fetched one unit ago has landed
           float x[KP];
-          gather_row<PH, PW, KP>(x, g < p.M, true, 2.f * c2, c2, zbuf + ((u & 1) * TM + pt) * D, PW);
+          gather_row<PH, PW, KP>(x, g < p.M, true, 2.f * c2, c2, zbuf + ((u % 3) * TM + pt) * D, PW);
           split_row<KP>(x, ahi, alo);
         } else {
           const int gg = min(g, p.P - 1), o = org[gg];
@@ -604,11 +616,6 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
       if (needA && pt < TM) asm volatile("" ::"f"(ahi[0]), "f"(ahi[24]), "f"(alo[24]), "f"(ahi[25]));  // loads landed
       if (pt == 32) CGP_TRACE(12, u);
 #endif
-      if (a_is_z && pt < TM && u + 1 < nun) {  // fetch the next unit's Z row (asynchronous, into shared memory)
-        UnitIter nx = it;
-        nx.next();
-        fetch_zrow(decode(mode, nx).arow + pt, (u + 1) & 1);
-      }
       // column weights of this unit.  Written before the slot wait below, when only the wait of unit u-1 is
       // behind us: MMA(u-3) was issued, hence the epilogue of unit u-5 is over -> an eight-deep ring
       // (a four-deep one let the epilogue of unit u-4 read the next tile's weights)
@@ -624,6 +631,13 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
       }
       if (pt == 32) CGP_TRACE(9, u);
       if (u >= 2) mbar_wait(&mma_done[u & 1], ((u >> 1) - 1) & 1);  // the MMAs of unit u-2 have read their operands
+      if (a_is_z && u + 1 < nun) {
+        // next unit's Z tile into buffer (u + 1) % 3, which held tile u-2: MMA(u-2) complete means every producer
+        // warp staged unit u-2, i.e. finished reading that buffer
+        UnitIter nx = it;
+        nx.next();
+        fetch_ztile(decode(mode, nx).arow, u + 1);
+      }
       if (pt == 32) CGP_TRACE(10, u);
       if (pt == 0) CGP_TRACE(13, u);
       if (needA) {
