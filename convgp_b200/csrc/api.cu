@@ -307,8 +307,11 @@ static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int
   CGP_CUDA_CHECK(cudaGetDevice(&dev));
 #define CALL(PH_, PW_)                                                                                        \
   {                                                                                                           \
-    auto kernel = (mode == 2 || mode == 4) ? umma::rowsum_kernel<PH_, PW_, true>                              \
-                                           : umma::rowsum_kernel<PH_, PW_, false>;                            \
+    void (*kernel)(const umma::Params) = mode == 0   ? umma::rowsum_kernel<PH_, PW_, 0>                       \
+                                         : mode == 1 ? umma::rowsum_kernel<PH_, PW_, 1>                       \
+                                         : mode == 2 ? umma::rowsum_kernel<PH_, PW_, 2>                       \
+                                         : mode == 3 ? umma::rowsum_kernel<PH_, PW_, 3>                       \
+                                                     : umma::rowsum_kernel<PH_, PW_, 4>;                      \
     {                                                                                                         \
       std::lock_guard<std::mutex> lk(g_launch_mu);                                                            \
       size_t& cur = g_launch_smem[std::make_pair((const void*)kernel, dev)];                                  \

@@ -437,10 +437,13 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // =====================================================================================
-// Row-sum kernel (modes 0-3, see the file header).  ARG2: also accumulate sum_c w_c k S (mode 2).
+// Row-sum kernel (modes 0-4, see the file header), one instantiation per mode: the producer path is a chain of
+// short dependent steps, and every run-time mode branch in it costs a branch-resolve bubble per unit.
+// ARG2 (modes 2, 4): also accumulate sum_c w_c k S.
 // =====================================================================================
-template <int PH, int PW, bool ARG2>
+template <int PH, int PW, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
+  constexpr bool ARG2 = MODE == 2 || MODE == 4;
   constexpr int D = PH * PW;
   constexpr int KP = pad_k(D);
   constexpr int KS = KP / 8;
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
   uint64_t* zbar = bars + 13;       // [3] Z-tile ring (mode 0): every producer's cp.async of the buffer has landed
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mode = p.mode;
+  constexpr int mode = MODE;
   const long long lo = p.n_units * blockIdx.x / gridDim.x;
   const long long hi = p.n_units * (blockIdx.x + 1) / gridDim.x;
   const int nun = (int)(hi - lo);
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
 
   const float lsv = p.ls[0], sig2 = p.var[0];
   const float c2 = 1.4426950408889634f / (2.f * lsv * lsv);
-  const bool a_is_z = mode == 0, b_is_z = mode == 3;
+  constexpr bool a_is_z = mode == 0, b_is_z = mode == 3;
 
   if (warp < kProd / 32) {
     // ============================== producers
@@ -557,7 +560,8 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
       const Unit un = decode(mode, it);
       if (pt == 0) CGP_TRACE(0, u);
       if (pt == 32) CGP_TRACE(8, u);
-      const bool needA = un.akey != akey, needB = un.bkey != bkey;
+      constexpr bool needA = true;  // a new A tile every unit (decode())
+      const bool needB = un.bkey != bkey;
       // (with a single unit per image the rings are only safe once unit u-2 is fully staged by everyone)
       if (units_per_image < 2 && u >= 2) mbar_wait(&mma_done[u & 1], ((u >> 1) - 1) & 1);
       if (un.n != cur_img) {
@@ -608,8 +612,9 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
           gather_row<PH, PW, KP>(x, g < p.M, true, 2.f * c2, c2, zbuf + ((u % 3) * TM + pt) * D, PW);
           split_row<KP>(x, ahi, alo);
         } else {
+          // rows past the last patch repeat it (finite values): their row sums are never stored
           const int gg = min(g, p.P - 1), o = org[gg];
-          load_patch_row<PH, PW, KP>(ahi, alo, g < p.P, true, shl + o, p.Wd, ehl[gg]);
+          load_patch_row<PH, PW, KP>(ahi, alo, true, true, shl + o, p.Wd, ehl[gg]);
         }
       }
 #ifdef CGP_UMMA_TRACE
@@ -668,8 +673,9 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
             gather_row<PH, PW, KP>(x, g < p.M, false, 1.f, c2, p.Z + (size_t)min(g, p.M - 1) * D, PW);
             split_row<KP>(x, xhi, xlo);
           } else {
+            // columns past the last patch repeat it (finite exponent): their column weight is zero
             const int gg = min(g, p.P - 1), o = org[gg];
-            load_patch_row<PH, PW, KP>(xhi, xlo, g < p.P, false, xhl + o, p.Wd, ehl[gg]);
+            load_patch_row<PH, PW, KP>(xhi, xlo, true, false, xhl + o, p.Wd, ehl[gg]);
           }
           put_row_smem<KP>(buf, TN, r, xhi, xlo);
         }
@@ -1170,7 +1176,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
       float bhi[KP], blo[KP];
       if (r >= 0) {
         const int g = brow + r, gg = min(g, p.P - 1), o = org[gg];
-        load_patch_row<PH, PW, KP>(bhi, blo, g < p.P, false, xhl + o, p.Wd, ehl[gg]);
+        load_patch_row<PH, PW, KP>(bhi, blo, true, false, xhl + o, p.Wd, ehl[gg]);  // past P: repeats, weight 0
       }
       if (pt < TN) {
         const int col = brow + pt;
