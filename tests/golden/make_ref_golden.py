@@ -57,6 +57,12 @@ def kernel_cases():
              xdist="uint8"),
         Case("ref_cifar_multi_c3", "multi", 32, 32, 3, 5, 5, [(1.0, 1.0, None, False)], N=2, M=12, seed=210,
              xdist="uint8"),
+        # BASELINE's full inducing sets (M = 750 / 1000: every row tile incl. the ragged last one) on a slice of the
+        # minibatch small enough for the reference's materialised (M x N P) tensor to fit in host memory
+        Case("ref_cfg3_mnist_wconv_M750", "conv", 28, 28, 1, 5, 5, [(1.0, 1.0, None, False)], N=24, M=750, seed=213),
+        Case("ref_cfg5_cifar_addwconv_M1000", "colour", 32, 32, 3, 5, 5,
+             [(1.004, 0.5, S[0::3], False), (0.991, 0.5, S[1::3], False), (1.013, 0.5, S[2::3], False)],
+             N=4, M=1000, seed=214, xdist="uint8"),
         # small geometries of the reference's tests (testing/test_convkerns.py:44-49, 104-110)
         Case("ref_tiny_2x2_c2", "conv", 3, 3, 2, 2, 2, [(1.0, 1.0, None, False)], N=3, M=8, seed=211, xdist="randn"),
         Case("ref_tiny_2x2_colour_c2", "colour", 3, 3, 2, 2, 2, [(1.0, 1.0, None, False)], N=3, M=8, seed=212,
@@ -106,6 +112,13 @@ def run_kernel_case(case, GP, ck, mi):
     # the eager NumPy entry points the reference's tests use
     assert np.array_equal(k.compute_Kzx(case.Z, case.X), out["kuf"])
     out["patches"] = k.compute_patches(case.X)[:1]  # first image: pins the patch layout
+    if case.M > 100:
+        # full inducing sets: keep the fixture small -- the inputs are regenerated from the Case's seed at test time
+        # (NumPy's legacy RandomState stream is stable), Kzz is kept on a sub-grid
+        for key in ("X", "Z", "W", "G", "gd", "Gu"):
+            del out[key]
+        out["kuu_sub"] = out.pop("kuu")[::7, ::5].copy()
+        out["x_checksum"] = np.array([case.X.sum(), case.Z.sum(), case.G.sum(), case.Gu.sum()])
     return out
 
 

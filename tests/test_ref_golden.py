@@ -24,9 +24,16 @@ EXTRA = ["ref_full_K", "ref_convrbf", "ref_conditional", "ref_models"]
 
 def _load(case):
     g = dict(np.load(os.path.join(REF_DIR, case.name + ".npz")))
-    case.X, case.Z, case.G, case.gd, case.Gu = g["X"], g["Z"], g["G"], g["gd"], g["Gu"]
-    case.Wv = g["W"] if case.weighted else None
+    if "X" in g:
+        case.X, case.Z, case.G, case.gd, case.Gu = g["X"], g["Z"], g["G"], g["gd"], g["Gu"]
+        case.Wv = g["W"] if case.weighted else None
+    else:  # full-M fixtures store outputs only: the Case regenerates the same seeded inputs
+        assert np.allclose([case.X.sum(), case.Z.sum(), case.G.sum(), case.Gu.sum()], g["x_checksum"], rtol=1e-14)
     return g
+
+
+def _kuu_err(kuu, g):
+    return rel_err(kuu[::7, ::5], g["kuu_sub"]) if "kuu_sub" in g else rel_err(kuu, g["kuu"])
 
 
 def _extra(name):
@@ -45,7 +52,7 @@ def test_oracle_matches_reference_source(case):
     ok = case.oracle_kernel()
     assert rel_err(ok.Kzx(case.Z, case.X), g["kuf"]) < 1e-12
     assert rel_err(ok.Kdiag(case.X), g["kdiag"]) < 1e-12
-    assert rel_err(ok.Kzz(case.Z), g["kuu"]) < 1e-12
+    assert _kuu_err(ok.Kzz(case.Z), g) < 1e-12
     assert np.array_equal(ok._get_patches(case.X[:1]), g["patches"])  # layout and values, bitwise
     ref = case.twin_grads()  # autodiff through OUR restatement vs autodiff through the reference's code
     assert rel_err(ref["dZ"], g["dZ"]) < 1e-11
@@ -129,7 +136,7 @@ def test_cuda_matches_reference_source(case, dtype):
     got = case.package_grads(dtype)
     assert rel_err(got["kuf"], g["kuf"]) < tol
     assert rel_err(got["kdiag"], g["kdiag"]) < tol
-    assert rel_err(got["kuu"], g["kuu"]) < tol
+    assert _kuu_err(got["kuu"], g) < tol
     assert rel_err(got["dZ"], g["dZ"]) < tol
     if case.weighted:
         assert rel_err(got["dW"], g["dW"]) < tol
