@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
   if (warp < kProd / 32) {
     // ============================== producers
     const int pt = tid;
-    int cur_img = -1, ki = -1, akey = -1, bkey = -1, aslot = 1, bslot = 1;
+    int cur_img = -1, ki = -1, akey = -1, bkey = -1, aslot = 1, bslot = 1, btile = -1;
     // Images stream through a three-deep cp.async ring with one mbarrier per buffer, and the arrays
     // derived from an image (split pixels, split patch norms) through a second three-deep ring: a
     // producer warp never meets the others at a CTA barrier (they run up to two units apart).
@@ -624,15 +624,11 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
       // column weights of this unit.  Written before the slot wait below, when only the wait of unit u-1 is
       // behind us: MMA(u-3) was issued, hence the epilogue of unit u-5 is over -> an eight-deep ring
       // (a four-deep one let the epilogue of unit u-4 read the next tile's weights)
-      if (pt >= kProd - TN) {
+      // (mode 3 only: there the weights are G[m, n] and change with the image; in the other modes they are the
+      // patch weights of the B tile and are written once per tile, with the tile, below)
+      if (b_is_z && pt >= kProd - TN) {
         const int c = pt - (kProd - TN), col = un.brow + c;
-        float v = 0.f;
-        if (b_is_z) {
-          if (col < p.M) v = p.G[(size_t)col * p.N + un.n];
-        } else if (col < p.P) {
-          v = w[col];
-        }
-        wc[(u & 7) * TN + c] = v;
+        wc[(u & 7) * TN + c] = col < p.M ? p.G[(size_t)col * p.N + un.n] : 0.f;
       }
       if (pt == 32) CGP_TRACE(9, u);
       if (u >= 2) mbar_wait(&mma_done[u & 1], ((u >> 1) - 1) & 1);  // the MMAs of unit u-2 have read their operands
@@ -663,7 +659,12 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
       if (needB) {  // warps 2-7
         bslot ^= 1;
         bkey = un.bkey;
+        ++btile;
         const int r = pt - (kProd - TN);
+        if (!b_is_z && r >= 0) {  // the tile's column weights: slot btile & 7 last held tile btile - 8
+          const int col = un.brow + r;
+          wc[(btile & 7) * TN + r] = col < p.P ? w[col] : 0.f;
+        }
         if (r >= 0) {
           unsigned char* buf = sB + bslot * 2 * B_HALF;
           const int g = un.brow + r;
@@ -742,7 +743,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)half * (TN / 2);
     float acc1, acc2;             // row sums of this unit (this thread's column half)
     float tvar = 0.f, tls = 0.f;  // mode 2: per-thread totals for dvariance / dlengthscale
-    int img_n = -1;
+    int img_n = -1, ebkey = -1, ebtile = -1;
     const float P2 = p.Pn * p.Pn;
     const float s_kuf = sig2 / p.Pn, s_kd = sig2 / P2;
     float* r1 = racc + half * 2 * Pp;  // this half's accumulators over the column tiles of an image
@@ -811,7 +812,12 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
       if (lane == 0 && half == 0) CGP_TRACE(20 + quarter, u);
       tc_fence_after();
       const uint32_t taddr = lane_addr + (uint32_t)(u & 1) * TN;
-      const float4* wc4 = reinterpret_cast<const float4*>(wc + (u & 7) * TN + half * (TN / 2));
+      if (un.bkey != ebkey) {
+        ebkey = un.bkey;
+        ++ebtile;
+      }
+      const float4* wc4 =
+          reinterpret_cast<const float4*>(wc + ((b_is_z ? u : ebtile) & 7) * TN + half * (TN / 2));
       uint32_t va[32], vb[32];
       auto process = [&](uint32_t (&v)[32], int c0) {
 #pragma unroll
