@@ -916,11 +916,13 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
 //
 // Flash-attention shaped: per unit (image n, tile of 192 patches) of one tile of 128 inducing rows
 //   GEMM1  S = Z . X^T            tf32 x3, A = Z tile (TMEM, resident), B = patches (shared memory)
-//   epilogue  coef = G[m,n]/P * w_p * ex2(S)   -> ONE fp16 term (scaled by a CTA-uniform power of two), written
-//             back over S in TMEM
-//   GEMM2  dz += coef . [X | 1]   kind::f16, A = coef from TMEM, B = X^T as two fp16 terms x1 | x2 plus a row of
-//          ones: column D of dz is sum_p coef from the SAME rounded coefficients, so dZ = sum coef (x - z) -- which
-//          cancels heavily -- sees only the relative rounding of each term (2^-12), not the cancellation
+//   epilogue  coef = G[m,n]/P * w_p * ex2(S)   -> two fp16 terms c1 + c2 (scaled by a CTA-uniform power of two),
+//             written back over S in TMEM, each 32-column chunk into the 32 columns it just vacated
+//   GEMM2  dz += coef . [X | 1]   kind::f16, A = c1 / c2 from TMEM, B = X^T as two fp16 terms x1 | x2 plus a row of
+//          ones (c1.x1 + c1.x2 + c2.x1): column D of dz is sum_p coef from the SAME rounded coefficients, so
+//          dZ = sum coef (x - z) -- which cancels -- sees only the relative rounding of each term.  One fp16 term
+//          (2^-12) is not enough: with patch weights of both signs the sum over patches itself cancels and a
+//          single-row dZ was off by 3e-4 (tools/fuzz_shapes.py, M = 1); two terms give <= 1e-6 there.
 // and at the end dZ = sigma^2 / l^2 (dz - z * sum coef).  A CTA owns one row tile for its whole life,
 // so the dz accumulator (64 TMEM columns) is read exactly once.  TMEM: S0 | S1 | dz | Z = 512 columns.
 // =====================================================================================
@@ -1260,7 +1262,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
     // ============================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t id1 = make_idesc(TM, TN, kFmtTF32);
-      constexpr uint32_t id2a = make_idesc(TM, 64, kFmtF16);
+      constexpr uint32_t id2a = make_idesc(TM, 64, kFmtF16), id2b = make_idesc(TM, 32, kFmtF16);
       const uint64_t dbh0 = make_desc(smem_u32(sB), 16 * TN, 128);
       const uint64_t dbt0 = make_desc(smem_u32(sBt), 16 * 64, 128);
       const uint32_t ah = tmem_base + kTmemA, al = ah + KP, d2 = tmem_base + kTmemD2;
@@ -1274,9 +1276,11 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int t = 0; t < 6; ++t) {
+          for (int t = 0; t < 6; ++t) {  // 16 patches per step; chunk c = t / 2 keeps c1 | c2 in its own 32 columns
             const uint64_t db = dbt + (uint64_t)(((h * 96 + t * 16) / 8) * ((16 * 64) >> 4));
-            mma_bf16_ts(d2, sc + h * 96 + 8 * t, db, id2a, (u | h | t) != 0);  // coef . [x1 | x2]
+            const uint32_t a1 = sc + h * 96 + 32 * (t >> 1) + 8 * (t & 1);
+            mma_bf16_ts(d2, a1, db, id2a, (u | h | t) != 0);  // c1 . [x1 | x2]   (x1 carries the ones row)
+            mma_bf16_ts(d2, a1 + 16, db, id2b, 1);            // c2 . x1
           }
         mma_commit(&g2_done[u % 3]);
         CGP_TRACE(13, u);
@@ -1371,7 +1375,7 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
         uint32_t v[32];
         tmem_ld32(tbuf + 32 * c, v);
         tmem_wait_ld(v);
-        uint32_t c1p[16];
+        uint32_t cp[32];  // this chunk's coefficients: c1 in packed columns [0, 16), the residual c2 in [16, 32)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 wq = wc4[8 * c + q];
@@ -1385,12 +1389,15 @@ __global__ void __launch_bounds__(kDzProd + 32 + kEpi, 1) kuf_dz_kernel(const Pa
             s2 = fmaf(cf[i], s, s2);
             v[4 * q + i] = __float_as_uint(c0);
           }
-          c1p[2 * q] = pack_f16x2(cf[1], cf[0]);
-          c1p[2 * q + 1] = pack_f16x2(cf[3], cf[2]);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const uint32_t a1 = pack_f16x2(cf[2 * h2 + 1], cf[2 * h2]);
+            cp[2 * q + h2] = a1;
+            cp[16 + 2 * q + h2] = pack_f16x2(cf[2 * h2 + 1] - f16_hi_to_f32(a1), cf[2 * h2] - f16_lo_to_f32(a1));
+          }
         }
-        // c1 of this chunk goes to packed columns 16 c .. 16 c + 15 of the half: already consumed
-        tmem_st8(tbuf + 16 * c, c1p);
-        tmem_st8(tbuf + 16 * c + 8, c1p + 8);
+        // both terms go back into the 32 columns this chunk just vacated
+        tmem_st32(tbuf + 32 * c, cp);
         if (do_dw) {
           // dW[p] = sigma^2 sum_{m, n} G[m, n] / P * k[m, n, p]: the sum over the tile's 128 rows is a column
           // sum across lanes (and the four lane quarters); lane L ends up with column 32 c + L of this half
