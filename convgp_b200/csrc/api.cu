@@ -259,7 +259,7 @@ static bool umma_ok(const cgp_kernel_desc* d, const Geo& g, int mode, int M) {
   if (mode != 1 || d->C != 1 || d->dtype != CGP_F32) return false;
   const int KP = umma::pad_k(g.D);
   const int racc_rows = std::max(g.P, (M + umma::TM - 1) / umma::TM * umma::TM);
-  return umma::smem_plan(KP, d->H * d->W, g.P, racc_rows).total <= 227 * 1024;
+  return umma::smem_plan(KP, d->H * d->W, g.P, racc_rows, M > 0 ? 3 : 0).total <= 227 * 1024;  // M > 0: Kuf (mode 0)
 }
 
 // mode: 0 Kuf fwd, 1 Kdiag fwd, 2 Kdiag bwd, 3 dW of Kuf (umma32.cuh)
@@ -300,7 +300,7 @@ static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int
   }
 #endif
   const int racc_rows = std::max(g.P, (M + umma::TM - 1) / umma::TM * umma::TM);
-  const size_t smem = umma::smem_plan(umma::pad_k(g.D), d->H * d->W, g.P, racc_rows).total;
+  const size_t smem = umma::smem_plan(umma::pad_k(g.D), d->H * d->W, g.P, racc_rows, mode == 0 ? 3 : 0).total;
   // one persistent CTA per SM walking a contiguous range of units
   const long long grid = std::max<long long>(1, std::min<long long>(p.n_units, num_sms()));
   int dev = 0;

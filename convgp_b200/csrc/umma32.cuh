@@ -403,7 +403,9 @@ constexpr int kIssuerWarp = kProd / 32, kEpiWarp0 = kProd / 32 + 1;
 struct Smem {
   int sB, wc, img, zbuf, w, org, racc, red, bars, total;
 };
-__host__ __device__ inline Smem smem_plan(int KP, int HW, int P, int R) {  // R: longest row-accumulator array
+// R: longest row-accumulator array; ztiles: raw Z tiles kept (3 in mode 0, the only mode that stages Z rows through
+// shared memory; 0 otherwise, which lets larger images fit the other modes)
+__host__ __device__ inline Smem smem_plan(int KP, int HW, int P, int R, int ztiles) {
   Smem s;
   int o = 0;
   s.sB = o;
@@ -412,8 +414,8 @@ __host__ __device__ inline Smem smem_plan(int KP, int HW, int P, int R) {  // R:
   o += 8 * TN * 4;
   s.img = o;  // 3 raw buffers (cp.async ring), then a 3-deep ring of derived arrays: xh, xl, sh, sl (HW), eh, el (P)
   o += 3 * ((HW * 4 + 15) / 16 * 16) + 3 * (4 * ((HW * 4 + 15) / 16 * 16) + 2 * ((P * 4 + 15) / 16 * 16));
-  s.zbuf = o;  // three raw Z tiles (mode 0): a cp.async ring, one mbarrier per buffer
-  o += 3 * TM * (KP - 2) * 4;
+  s.zbuf = o;  // raw Z tiles (mode 0): a cp.async ring, one mbarrier per buffer
+  o += ztiles * TM * (KP - 2) * 4;
   s.w = o;
   o += (P * 4 + 15) / 16 * 16;
   s.org = o;  // patch index -> offset of its origin in the image (no integer division in the unit loop: the
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int HW = p.H * p.Wd;
   const int Racc = max(p.P, (p.M + TM - 1) / TM * TM);
-  const Smem L = smem_plan(KP, HW, p.P, Racc);
+  const Smem L = smem_plan(KP, HW, p.P, Racc, MODE == 0 ? 3 : 0);
   unsigned char* sB = smem + L.sB;
   float* wc = reinterpret_cast<float*>(smem + L.wc);
   float* img0 = reinterpret_cast<float*>(smem + L.img);
