@@ -1,32 +1,33 @@
 // float32 kernels on the 5th-generation tensor cores: tcgen05.mma (UMMA) with TMEM accumulators.
 //
 // The patch-vs-patch / patch-vs-inducing contraction is a GEMM with a tiny inner dimension
-// (D = 25 -> 32): S = A . B^T with A, B staged in shared memory in the UMMA no-swizzle K-major
-// ("interleaved") layout, accumulated in TMEM by tcgen05.mma.kind::tf32 with the 3xTF32 split
-// (x = x_hi + x_lo; a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi, <= 3e-6 -- a single TF32 product
-// breaks the 1e-4 tolerance).  Two spare inner-dimension slots carry the row and
-// column norms, so the accumulator IS the RBF exponent in log2 units:
+// (D = 25 -> 32): S = A . B^T, A (128 rows) written from registers into TMEM (tcgen05.st), B (192 rows)
+// staged in shared memory in the UMMA no-swizzle K-major ("interleaved") layout, accumulated in TMEM by
+// tcgen05.mma.kind::tf32 with the 3xTF32 split (x = x_hi + x_lo; a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi,
+// <= 3e-6 -- a single TF32 product breaks the 1e-4 tolerance).  Two spare inner-dimension
+// slots carry the row and column norms, so the accumulator IS the RBF exponent in log2 units:
 //     S[r, c] = c2 * (2 a_r.b_c - |a_r|^2 - |b_c|^2),   c2 = log2(e) / (2 l^2)
 //     k[r, c] = ex2(S[r, c])                            (one MUFU per pair)
-// A 128 x 192 tile of S lives in TMEM (two buffers: the MMAs of tile u+1 overlap the epilogue of
-// tile u); four epilogue warps pull it with tcgen05.ld, exponentiate and reduce along the row in
-// registers.  The N x P x M tensor the reference materialises (convkernels.py:82-87, :183-190)
-// never leaves the SM.
+// A 128 x 192 tile of S lives in TMEM (two buffers: the MMAs of tile u+1 overlap the epilogue of tile u);
+// eight epilogue warps pull it with tcgen05.ld, exponentiate and reduce along the row in registers.  The
+// N x P x M tensor the reference materialises (convkernels.py:82-87, :183-190) never leaves the SM.
 //
-// Warp roles (288 threads): warps 0-3 epilogue (TMEM lane quarter = warp), warps 4-7 producers
-// (gather patches straight from the staged image / scale inducing rows, split hi/lo, write UMMA
-// layout), warp 8 lane 0 issues the MMAs.  mbarriers: staged[2] (producers -> issuer),
-// mma_done[2] (tcgen05.commit -> epilogue and producers), tmem_empty[2] (epilogue -> issuer).
+// Warp roles (512 threads, one persistent CTA per SM): warps 0-6 producers (gather patches straight from the
+// image staged and pre-split in shared memory / scale and split inducing rows, write TMEM and the UMMA layout),
+// warp 7 lane 0 issues the MMAs, warps 8-15 epilogue (TMEM lane quarter = warp % 4, column half = (warp - 8) / 4).
+// mbarriers: staged[2] (producers -> issuer), mma_done[2] (tcgen05.commit -> epilogue and producers),
+// tmem_empty[2] (epilogue -> issuer), and cp.async rings for the images, their derived arrays and the Z tiles.
 //
-// One kernel, five uses ("row-sum" modes; rows = TMEM lanes, columns weighted and summed):
+// One kernel, five uses ("row-sum" modes, one instantiation each; rows = TMEM lanes, columns weighted and summed):
 //   0  Kuf forward   rows = inducing patches, cols = patches of image n, weights w_p
 //   1  Kdiag forward rows = patches of image n, cols = patches of image n, weights w_p'
 //   2  Kdiag backward: same tiles, also accumulates sum_c w_c k S for dlengthscale
-//   3  dW of Kuf     rows = patches of image n, cols = inducing patches, weights G[m, n]
+//   3  dW of Kuf     rows = patches of image n, cols = inducing patches, weights G[m, n]  (tested variant; the
+//      default takes dW from kuf_dz_kernel)
 //   4  Kdiag forward that also saves, per image, the row sums and the two totals its backward is made of
 //      (api.cu: cgp_kdiag_fwd_saved / cgp_kdiag_bwd_saved) -- the backward then never revisits the P x P Gram
-// and a second kernel (kuf_dz_kernel) for the dZ / dvariance / dlengthscale part of Kuf backward,
-// which feeds the coefficients back through TMEM as the A operand of a second GEMM.
+// and a second kernel (kuf_dz_kernel) for the whole Kuf backward (dZ, dW, dvariance, dlengthscale), which feeds
+// the coefficients back through TMEM as the A operand of a second GEMM.
 #pragma once
 #include "common.cuh"
 
