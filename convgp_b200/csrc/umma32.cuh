@@ -925,7 +925,7 @@ __global__ void __launch_bounds__(kThreads, 1) rowsum_kernel(const Params p) {
 //          ones (c1.x1 + c1.x2 + c2.x1): column D of dz is sum_p coef from the SAME rounded coefficients, so
 //          dZ = sum coef (x - z) -- which cancels -- sees only the relative rounding of each term.  One fp16 term
 //          (2^-12) is not enough: with patch weights of both signs the sum over patches itself cancels and a
-//          single-row dZ was off by 3e-4 (tools/fuzz_shapes.py, M = 1); two terms give <= 1e-6 there.
+//          single-row dZ was off by 3e-4 (tests/tools/fuzz_shapes.py, M = 1); two terms give <= 1e-6 there.
 // and at the end dZ = sigma^2 / l^2 (dz - z * sum coef).  A CTA owns one row tile for its whole life,
 // so the dz accumulator (64 TMEM columns) is read exactly once.  TMEM: S0 | S1 | dz | Z = 512 columns.
 // =====================================================================================

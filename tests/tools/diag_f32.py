@@ -1,6 +1,6 @@
 """Development aid: where does the float32 path differ from the float64 path at full size?"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from tests.test_gpu_parity import full_size_case
 from tests.util import rel_err

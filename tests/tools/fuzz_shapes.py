@@ -1,12 +1,12 @@
 """Development aid: randomised geometry sweep of the default CUDA families against the NumPy oracle / torch twin
-(values and gradients, both dtypes).  python tools/fuzz_shapes.py [n_cases] [seed]"""
+(values and gradients, both dtypes).  python tests/tools/fuzz_shapes.py [n_cases] [seed]"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tests.util import Case, rel_err  # noqa: E402
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40

@@ -1,7 +1,7 @@
 """Development aid: first-call-in-process check of the float64 dW pieces (fuzz0 geometry)."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tests.util import Case, rel_err
 import oracle.torch_twin as T
 from convgp_b200.kernels import as_tensor

@@ -1,7 +1,7 @@
 """Development aid: hash the CPU twin's and the CUDA path's float64 dW (Kuf only) in a fresh process."""
 import hashlib, os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tests.util import Case
 import oracle.torch_twin as T
 from convgp_b200.kernels import as_tensor
