@@ -108,6 +108,22 @@ class Case:
 
     # ---- torch twin: values + autograd gradients of <G,Kuf> + <gd,Kdiag> + <Gu,Kuu>
     def twin_grads(self, dtype=torch.float64):
+        """The twin's gradients, evaluated until two evaluations agree bit for bit: torch's CPU result was seen to
+        move by ~1e-9 in a small fraction of evaluations on a loaded host, which matters at the
+        1e-10 / 1e-11 tolerances used against it."""
+        def same(a, b):
+            return all(np.array_equal(a[k], b[k]) for k in ("kuf", "kdiag", "kuu", "dZ")) and \
+                (a["dW"] is None or np.array_equal(a["dW"], b["dW"])) and \
+                all(np.array_equal(x, y) for x, y in zip(a["dvar"] + a["dls"], b["dvar"] + b["dls"]))
+        prev = self._twin_grads_once(dtype)
+        for _ in range(3):
+            cur = self._twin_grads_once(dtype)
+            if same(prev, cur):
+                return cur
+            prev = cur
+        return prev
+
+    def _twin_grads_once(self, dtype=torch.float64):
         g = self.geom
         X = torch.tensor(self.X, dtype=dtype)
         Z = torch.tensor(self.Z, dtype=dtype, requires_grad=True)
