@@ -245,6 +245,21 @@ def run_models(GP, ck, mi, ss, sc):
     mu, var = m.predict_f(X)
     out.update(svc_X=X, svc_Y=Y, svc_Z=Z, svc_q_mu=q_mu, svc_q_sqrt=q_sqrt, svc_mu=mu, svc_var=var,
                svc_elbo=m.compute_log_likelihood(), svc_patch_mu=m.compute_patch_predictions(X))
+
+    # -- SVColourConvGP (svconvgp.py:25-63): one conv kernel applied per colour channel, outputs mixed by wc
+    rng = np.random.RandomState(233)
+    N, M, L, C = 5, 6, 2, 3
+    X, Y, Z = rng.rand(N, 64 * C), rng.randn(N, L), rng.rand(M, 9)
+    k = ck.WeightedConv(GP.kernels.RBF(9, variance=0.8, lengthscales=1.2), [8, 8], [3, 3])
+    Wk = rng.rand(36) + 0.5
+    k.W = Wk
+    m = sc.SVColourConvGP(X, Y, k, GP.likelihoods.Gaussian(), Z, C, num_latent=L)
+    wc = rng.rand(C) + 0.5
+    m.wc = wc
+    q_mu, q_sqrt = _variational(rng, M, L * C)
+    m.q_mu, m.q_sqrt = q_mu, q_sqrt
+    mu, var = m.predict_f(X)
+    out.update(scc_X=X, scc_Y=Y, scc_Z=Z, scc_W=Wk, scc_wc=wc, scc_q_mu=q_mu, scc_q_sqrt=q_sqrt, scc_mu=mu, scc_var=var)
     return out
 
 
@@ -268,18 +283,24 @@ def prepare(case):
     return case
 
 
-def main():
+def main(only=()):
+    """Regenerate every fixture, or only the named ones (`python tests/golden/make_ref_golden.py ref_models`)."""
     from oracle import run_reference as R
     GP, ck, mi, ss, sc = R.load()
     os.makedirs(OUT, exist_ok=True)
     for case in kernel_cases():
+        if only and case.name not in only:
+            continue
         np.savez_compressed(os.path.join(OUT, case.name + ".npz"), **run_kernel_case(prepare(case), GP, ck, mi))
         print("wrote", case.name)
-    for name, d in (("ref_full_K", run_full_K(GP, ck, mi)), ("ref_convrbf", run_convrbf(GP, ck)),
-                    ("ref_conditional", run_conditional(mi)), ("ref_models", run_models(GP, ck, mi, ss, sc))):
-        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    for name, fn in (("ref_full_K", lambda: run_full_K(GP, ck, mi)), ("ref_convrbf", lambda: run_convrbf(GP, ck)),
+                     ("ref_conditional", lambda: run_conditional(mi)),
+                     ("ref_models", lambda: run_models(GP, ck, mi, ss, sc))):
+        if only and name not in only:
+            continue
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **fn())
         print("wrote", name)
 
 
 if __name__ == "__main__":
-    main()
+    main(tuple(sys.argv[1:]))

@@ -230,3 +230,11 @@ def test_cuda_models_match_reference_source():
     assert rel_err(mu, g["svc_mu"]) < 1e-9 and rel_err(var, g["svc_var"]) < 1e-8
     assert abs(m.compute_log_likelihood() - float(g["svc_elbo"])) < 1e-8 * abs(float(g["svc_elbo"]))
     assert rel_err(m.compute_patch_predictions(g["svc_X"]), g["svc_patch_mu"]) < 1e-9
+    # SVColourConvGP (svconvgp.py:25-63)
+    k = ck.WeightedConv(bk.RBF(9, variance=0.8, lengthscales=1.2), [8, 8], [3, 3])
+    k.W = g["scc_W"]
+    m = svconvgp.SVColourConvGP(g["scc_X"], g["scc_Y"], k, lik.Gaussian(1.0), g["scc_Z"], 3, num_latent=2)
+    m.wc = g["scc_wc"]
+    m.q_mu, m.q_sqrt = g["scc_q_mu"], g["scc_q_sqrt"]
+    mu, var = m.predict_f(g["scc_X"])
+    assert rel_err(mu, g["scc_mu"]) < 1e-9 and rel_err(var, g["scc_var"]) < 1e-9
