@@ -94,3 +94,19 @@ def svconvgp_predict_bruteforce(basekern, Z, X, q_mu, q_sqrt, img_size, patch_si
         mus.append(fmean.sum(0))
         vars_.append(out_v)
     return np.array(mus), np.array(vars_)
+
+
+def svcolourconvgp_predict(kern, Z, X, q_mu, q_sqrt, wc, L, C, jitter=1e-5):
+    """svconvgp.py:47-63: the same kernel applied to every colour channel of the image (pixel-major, channel-minor
+    input), one set of variational parameters per channel, outputs mixed by ``wc``."""
+    M = Z.shape[0]
+    Xc = X.reshape(X.shape[0], -1, C)
+    qm, qs = q_mu.reshape(M, L, C), q_sqrt.reshape(M, M, L, C)
+    Kmm = kern.Kzz(Z) + jitter * np.eye(M)
+    mu, var = 0, 0
+    for c in range(C):
+        Xch = np.ascontiguousarray(Xc[:, :, c])
+        m, v = O.conditional(kern.Kdiag(Xch), kern.Kzx(Z, Xch), Kmm, qm[:, :, c], qs[:, :, :, c], True)
+        mu, var = mu + wc[c] * m, var + wc[c] * v
+    return mu, var
+

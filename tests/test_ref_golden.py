@@ -124,6 +124,11 @@ def test_oracle_models_match_reference_source():
                                              g["svc_q_sqrt"], [28, 28], 5)
     assert rel_err(mu, g["svc_mu"]) < 1e-11 and rel_err(var, g["svc_var"]) < 1e-10
     assert np.array_equal(O.Conv(O.RBF(25), [28, 28], [5, 5])._get_patches(g["svc_X"])[:, 0, :], g["svc_Zinit"])
+    # SVColourConvGP (svconvgp.py:47-63)
+    k = O.WeightedConv(O.RBF(9, 0.8, 1.2), [8, 8], [3, 3])
+    k.W = g["scc_W"]
+    mu, var = SO.svcolourconvgp_predict(k, g["scc_Z"], g["scc_X"], g["scc_q_mu"], g["scc_q_sqrt"], g["scc_wc"], 2, 3)
+    assert rel_err(mu, g["scc_mu"]) < 1e-11 and rel_err(var, g["scc_var"]) < 1e-11
 
 
 # ------------------------------------------------------------------------------------------- GPU: CUDA path
