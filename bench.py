@@ -2,17 +2,19 @@
 """Benchmark of the convgp patch-kernel hot path (BASELINE.json metric):
 
     conv/wconv Kuf + Kdiag (+ Kuu) forward + backward, images/s, 28x28, 5x5 patches, M=750,
-    minibatch 200 per GPU (config 3: mnist.py -k wconv -M 750 --minibatch-size 200), float64 (default)
-    or float32.
+    minibatch 200 (config 3: mnist.py -k wconv -M 750 --minibatch-size 200), float64 AND float32.
 
-One "step" = one pass of the hot path over one minibatch: Kuf, Kdiag, Kuu forward, then their
-backward w.r.t. Z, W, variance, lengthscales from given upstream gradients.
-N>1: one process per GPU (torchrun), each rank runs the step on its own 200 images (weak scaling)
-and the packed gradient buffer is all-reduced over NCCL every step inside the timed region.
+One "step" = one pass of the hot path over one minibatch: Kuf, Kdiag, Kuu forward, then -- after a join, because
+dL/dKuf depends on all three forwards in the reference's ELBO -- their backward w.r.t. Z, W, variance, lengthscales
+from given upstream gradients.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f64|f32] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype both|f64|f32] [--impl reference]
+                  [--secondary / --no-secondary] [--workload hotpath|predict]
 
-Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for how each field is obtained.
+Prints ONE JSON line (rank 0): the float64 headline, an "f32" sub-object with the tcgen05 path, the secondary
+configs under "configs", the SVGP training step under "svgp_step", and for N > 1 "strong" (the same 200 images
+split by rows, all-reduce inside the timed region) and "grad_check" (all-reduced sharded gradient vs rank 0's
+unsharded gradient) next to the weak-scaling headline.  See DESIGN.md section 6 for how each field is obtained.
 """
 import argparse
 import json
@@ -27,106 +29,164 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H = W_IMG = 28
-PH = PW = 5
-M_IND = 750
-N_BATCH = 200
-P = (H - PH + 1) * (W_IMG - PW + 1)  # 576
-D = PH * PW  # 25
-WORKLOAD = "mnist.py -k wconv -M 750 --minibatch-size 200 (28x28x1, 5x5 patches, P=576, D=25)"
+
+# ----------------------------------------------------------------------------- workloads
+class Cfg:
+    """One BASELINE.json configuration of the hot path.  groups: [(variance, lengthscale)] of the additive RBF base
+    kernel; layout 'planar' (Conv._get_patches) or 'colour' (ColourPatchConv._get_patches)."""
+
+    def __init__(self, key, workload, H, W, C, ph, pw, layout, M, N, weighted, groups, white, xdist="rand"):
+        self.key, self.workload = key, workload
+        self.H, self.W, self.C, self.ph, self.pw, self.layout = H, W, C, ph, pw, layout
+        self.M, self.N, self.weighted, self.groups, self.white, self.xdist = M, N, weighted, groups, white, xdist
+        self.Pc = (H - ph + 1) * (W - pw + 1)
+        if layout == "planar":
+            self.P, self.D = self.Pc * C, ph * pw
+        else:
+            self.P, self.D = self.Pc, ph * pw * C
+        self.G = len(groups)
+        self.diag_add = white + 1e-5  # White variance (mnist.py:42) + jitter (gpflowrc:11)
 
 
-# ----------------------------------------------------------------------------- workload
-def im2col(X):
+def _cifar_groups():
+    r = np.random.default_rng(2)
+    return [(1.0 + 0.01 * r.standard_normal(), 0.5) for _ in range(3)]  # cifar.py:36-37
+
+
+CONFIGS = {
+    "cfg1": Cfg("cfg1", "rectangles.py -k conv -M 16 --minibatch-size 100 (28x28x1, 3x3 patches, P=676, D=9)",
+                28, 28, 1, 3, 3, "planar", 16, 100, False, [(1.0, 1.0)], 1e-3),
+    "cfg2": Cfg("cfg2", "mnist01.py -k wconv -M 50 (28x28x1, 5x5 patches, P=576, D=25, minibatch 100)",
+                28, 28, 1, 5, 5, "planar", 50, 100, True, [(1.0, 1.0)], 1e-3),
+    "cfg3": Cfg("cfg3", "mnist.py -k wconv -M 750 --minibatch-size 200 (28x28x1, 5x5 patches, P=576, D=25)",
+                28, 28, 1, 5, 5, "planar", 750, 200, True, [(1.0, 1.0)], 1e-3),
+    # the patch-kernel half of sumkern_mnist.py (k1 = WeightedConv(RBF(25)), no White: sumkern_mnist.py:32); the
+    # RBF(784) half and the 1500 x 1500 variational covariance are in "svgp_step" (model level)
+    "cfg4": Cfg("cfg4", "sumkern_mnist.py -k1 wconv -k2 rbf -M 750 --vardist full --minibatch-size 200: k1 patch kernels",
+                28, 28, 1, 5, 5, "planar", 750, 200, True, [(1.0, 1.0)], 0.0),
+    "cfg5": Cfg("cfg5", "cifar.py -k addwconv -M 1000 --minibatch-size 30 (32x32x3 colour patches, 5x5, P=784, "
+                        "D=75 = 3 RBF groups x 25)",
+                32, 32, 3, 5, 5, "colour", 1000, 30, True, _cifar_groups(), 0.0, xdist="uint8"),
+}
+HEAD = CONFIGS["cfg3"]
+METRIC = "conv/wconv Kuf+Kdiag fwd+bwd images/sec (28x28, M=750)"
+
+
+def im2col(X, cfg):
+    """NumPy patches (N, P, D) in the reference's two layouts (convkernels.py:38-62, :128-141)."""
     N = X.shape[0]
-    img = X.reshape(N, H, W_IMG)
-    out = np.empty((N, H - PH + 1, W_IMG - PW + 1, PH, PW))
-    for i in range(PH):
-        for j in range(PW):
-            out[:, :, :, i, j] = img[:, i:i + H - PH + 1, j:j + W_IMG - PW + 1]
-    return out.reshape(N, P, D)
+    Ho, Wo = cfg.H - cfg.ph + 1, cfg.W - cfg.pw + 1
+    if cfg.layout == "planar":
+        img = X.reshape(N, cfg.H * cfg.W, cfg.C).transpose(0, 2, 1).reshape(N * cfg.C, cfg.H, cfg.W)
+        out = np.empty((N * cfg.C, Ho, Wo, cfg.ph, cfg.pw))
+        for i in range(cfg.ph):
+            for j in range(cfg.pw):
+                out[:, :, :, i, j] = img[:, i:i + Ho, j:j + Wo]
+        return out.reshape(N, cfg.C * Ho * Wo, cfg.ph * cfg.pw)
+    img = X.astype(np.float32).astype(np.float64).reshape(N, cfg.H, cfg.W, cfg.C)
+    out = np.empty((N, Ho, Wo, cfg.ph, cfg.pw, cfg.C))
+    for i in range(cfg.ph):
+        for j in range(cfg.pw):
+            out[:, :, :, i, j, :] = img[:, i:i + Ho, j:j + Wo, :]
+    return out.reshape(N, Ho * Wo, cfg.ph * cfg.pw * cfg.C)
 
 
-def make_inputs(rank, n_images=N_BATCH):
-    """Seeded synthetic inputs of config 3: X ~ U[0,1) (seed 0+rank), Z = M patches of X + 1e-3 U
-    (seed 1), l = 1, var = 1, W = 1, upstream gradients ~ N(0,1) (seeds 4,5,6)."""
-    X = np.random.default_rng(0 + rank).random((n_images, H * W_IMG))
+def _draw_x(cfg, seed, n):
+    r = np.random.default_rng(seed)
+    if cfg.xdist == "uint8":
+        return r.integers(0, 256, size=(n, cfg.H * cfg.W * cfg.C)) / 255.0
+    return r.random((n, cfg.H * cfg.W * cfg.C))
+
+
+def make_inputs(cfg, rank=0, n_images=None):
+    """Seeded synthetic inputs: X ~ U[0,1) (seed 0+rank; uint8/255 for config 5), Z = M patches of
+    the seed-0 minibatch + 1e-3 U (seed 1), W = 1, upstream gradients ~ N(0,1) (seeds 4,5,6)."""
+    n = cfg.N if n_images is None else n_images
+    X = _draw_x(cfg, 0 + rank, n)
     r1 = np.random.default_rng(1)
-    pat = im2col(np.random.default_rng(0).random((N_BATCH, H * W_IMG))).reshape(-1, D)
-    Z = pat[r1.permutation(len(pat))[:M_IND]] + 0.001 * r1.random((M_IND, D))
-    G = np.random.default_rng(4).standard_normal((M_IND, n_images))
-    gd = np.random.default_rng(5).standard_normal(n_images)
-    Gu = np.random.default_rng(6).standard_normal((M_IND, M_IND))
-    return dict(X=X, Z=Z, W=np.ones(P), var=np.array([1.0]), ls=np.array([1.0]), G=G, gd=gd, Gu=Gu)
+    pat = im2col(_draw_x(cfg, 0, min(cfg.N, 64)), cfg).reshape(-1, cfg.D)
+    Z = pat[r1.permutation(len(pat))[:cfg.M]] + 0.001 * r1.random((cfg.M, cfg.D))
+    G = np.random.default_rng(4).standard_normal((cfg.M, n))
+    gd = np.random.default_rng(5).standard_normal(n)
+    Gu = np.random.default_rng(6).standard_normal((cfg.M, cfg.M))
+    return dict(X=X, Z=Z, W=np.ones(cfg.P) if cfg.weighted else None, var=np.array([g[0] for g in cfg.groups]),
+                ls=np.array([g[1] for g in cfg.groups]), G=G, gd=gd, Gu=Gu)
 
 
-def algorithmic_work(n_images):
-    """FMA-pipe flops and exps of one step (SURVEY.md 8d): per unique pair, forward 2D+2 flops + 1 exp;
-    backward 4D+8 (Kuf) / 2D+8 (Kdiag) flops + 1 exp (recompute)."""
-    kuf = n_images * P * M_IND
+def algorithmic_work(cfg, n_images):
+    """FMA-pipe flops and exps of one step: per unique pair with G_k RBF groups over D dims, forward
+    2D+2G_k flops + G_k exps; backward 4D+8G_k (Kuf) / 2D+8G_k (Kdiag) flops + G_k exps (recompute)."""
+    D, G, P, M = cfg.D, cfg.G, cfg.P, cfg.M
+    kuf = n_images * P * M
     kdiag = n_images * P * (P + 1) // 2
-    kuu = M_IND * M_IND
+    kuu = M * M
     w = {
-        "kuf_fwd": (kuf * (2 * D + 2), kuf), "kdiag_fwd": (kdiag * (2 * D + 2), kdiag),
-        "kuu_fwd": (kuu * (2 * D + 2), kuu), "kuf_bwd": (kuf * (4 * D + 8), kuf),
-        "kdiag_bwd": (kdiag * (2 * D + 8), kdiag), "kuu_bwd": (kuu * (4 * D + 8), kuu),
+        "kuf_fwd": (kuf * (2 * D + 2 * G), kuf * G), "kdiag_fwd": (kdiag * (2 * D + 2 * G), kdiag * G),
+        "kuu_fwd": (kuu * (2 * D + 2 * G), kuu * G), "kuf_bwd": (kuf * (4 * D + 8 * G), kuf * G),
+        "kdiag_bwd": (kdiag * (2 * D + 8 * G), kdiag * G), "kuu_bwd": (kuu * (4 * D + 8 * G), kuu * G),
     }
     w["step"] = (sum(v[0] for v in w.values()), sum(v[1] for v in w.values()))
-    # algorithmic HBM bytes/step: X read fwd+bwd, Z, Kuf out + G in, small vectors
     return w
 
 
-def algorithmic_bytes(n_images, es):
-    return es * (2 * n_images * H * W_IMG + 4 * M_IND * D + 2 * M_IND * n_images + 2 * M_IND * M_IND + 4 * P
-                 + 2 * n_images)
+def algorithmic_bytes(cfg, n_images, es):
+    """HBM bytes one fused step has to move: X read forward + backward, Z, Kuf out + G in, Kuu + Gu, small vectors."""
+    return es * (2 * n_images * cfg.H * cfg.W * cfg.C + 4 * cfg.M * cfg.D + 2 * cfg.M * n_images
+                 + 2 * cfg.M * cfg.M + 4 * cfg.P + 2 * n_images)
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def cpu_port_images_per_s(dtype_name, n_images, reps, threads=None):
-    """The reference's algorithm on host cores: oracle/torch_twin (materialised patches -> GEMM ->
-    exp -> patch sums, per-image Kdiag loop, autodiff backward)."""
+def cpu_port_images_per_s(cfg, dtype_name, n_images, reps, threads=None):
+    """The reference's algorithm on host cores: oracle/torch_twin (materialised patches -> GEMM -> exp -> patch
+    sums, per-image Kdiag loop, autodiff backward).  The only place bench.py executes oracle/."""
     import torch
     from oracle import torch_twin as T
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     dt = torch.float64 if dtype_name == "f64" else torch.float32
-    inp = make_inputs(0, n_images)
-    g = T.Geom(H, W_IMG, 1, PH, PW, "conv")
+    inp = make_inputs(cfg, 0, n_images)
+    g = T.Geom(cfg.H, cfg.W, cfg.C, cfg.ph, cfg.pw, "conv" if cfg.layout == "planar" else "colour")
     X = torch.tensor(inp["X"], dtype=dt)
     G, gd, Gu = (torch.tensor(inp[k], dtype=dt) for k in ("G", "gd", "Gu"))
     times = []
     for rep in range(reps + 1):
         Z = torch.tensor(inp["Z"], dtype=dt, requires_grad=True)
-        Wt = torch.tensor(inp["W"], dtype=dt, requires_grad=True)
-        v = torch.tensor(1.0, dtype=dt, requires_grad=True)
-        l = torch.tensor(1.0, dtype=dt, requires_grad=True)
+        Wt = None if inp["W"] is None else torch.tensor(inp["W"], dtype=dt, requires_grad=True)
+        groups = []
+        for gi, (v, l) in enumerate(cfg.groups):
+            ad = None if cfg.G == 1 else torch.arange(gi, cfg.D, cfg.G)
+            groups.append((torch.tensor(float(v), dtype=dt, requires_grad=True),
+                           torch.tensor(float(l), dtype=dt, requires_grad=True), ad))
         t0 = time.perf_counter()
-        T.hot_path_step(X, Z, [(v, l, None)], g, Wt, G, gd, Gu, chunk=8)
+        T.hot_path_step(X, Z, groups, g, Wt, G, gd, Gu, chunk=8)
         dt_s = time.perf_counter() - t0
-        if rep > 0:  # first pass is warm-up
+        if rep > 0 or reps == 0:  # first pass is warm-up (unless it is the only one asked for)
             times.append(dt_s)
     return n_images / statistics.median(times), threads, times
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle/torch_twin port; the TF1/GPflow stack cannot be
+    installed) on ALL host cores, on the full minibatch of the headline configuration, W warm-up + K timed steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 40
-    per_step = []
+    cfg = HEAD
+    dtype = "f64" if args.dtype == "both" else args.dtype
     total = args.steps + args.warmup
-    v, threads, times = cpu_port_images_per_s(args.dtype, sample, max(1, total - 1))
+    v, threads, times = cpu_port_images_per_s(cfg, dtype, cfg.N, max(0, total - 1))
     times = times[-args.steps:] if len(times) >= args.steps else times
     ms = 1e3 * statistics.mean(times)
-    value = sample / (ms * 1e-3)
+    value = cfg.N / (ms * 1e-3)
     line = {
-        "impl": "reference", "metric": "conv/wconv Kuf+Kdiag fwd+bwd images/sec (28x28, M=750)", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_step": sample,
-                   "note": "reference TF1/GPflow stack not installable; oracle/torch_twin (same algorithm) on host cores"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": cfg.workload, "images_per_gpu_per_step": cfg.N, "M": cfg.M,
+                   "note": "reference TF1/GPflow stack not installable; oracle/torch_twin (same algorithm) on host cores, "
+                           "the full %d-image minibatch per step" % cfg.N},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": "%d images per step of the %d-image minibatch, M=750, fwd+bwd" % (sample, N_BATCH)},
+                         "sample": "the full %d-image minibatch per step, M=%d, fwd+bwd" % (cfg.N, cfg.M)},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -186,105 +246,206 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def run_gpu(args):
-    import torch
-    import torch.distributed as dist
-    from convgp_b200 import _lib
-    from convgp_b200.hotpath import HotPath
+class Ctx:
+    """Per-process state of the GPU arm: device, ranks, flush buffer, probed pipe peaks, the gradient collective."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
-                         "(use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
-    dt = torch.float64 if args.dtype == "f64" else torch.float32
-    es = 8 if args.dtype == "f64" else 4
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                             "(use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: ONE JSON line
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.peaks = {}
+        self.launches = 0
 
-    inp = make_inputs(rank)
-    tens = {k: torch.tensor(v, dtype=dt, device=dev) for k, v in inp.items()}
-    spec = _lib.Spec(dt, H, W_IMG, 1, PH, PW, _lib.LAYOUT_PLANAR, _lib.OUT_SUM, 1, False, False)
-    hp = HotPath(spec, tens["X"], tens["Z"], tens["W"], tens["var"], tens["ls"], tens["G"], tens["gd"], tens["Gu"],
-                 diag_add=1e-3 + 1e-5)  # White(1, 1e-3) + jitter (mnist.py:42, gpflowrc:11)
-    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    def flush_l2(self):
+        self.flush_buf.fill_(self.rank & 0xFF)
 
-    def flush_l2():
-        flush_buf.fill_(rank & 0xFF)
-
-    def allreduce():
-        if world > 1:
-            dist.all_reduce(hp.grads)
-
-    # ---- peaks of the binding pipes, measured on this box (MEASURED_PEAKS.json has HBM / bf16 only)
-    import ctypes
-    peaks = {}
-    if rank == 0:
-        for kind, name in ((0, "fp64_fma"), (1, "fp32_fma"), (2, "mufu_ex2"), (3, "f64_exp"), (4, "fp64_mma"), (16, "tf32_mma"),
-                           (17, "tcgen05_tf32")):
+    def probe_peaks(self):
+        """Pipe rates of this GPU (MEASURED_PEAKS.json has HBM / bf16 only, neither bounds this path)."""
+        import ctypes
+        from convgp_b200 import _lib
+        if self.peaks or self.rank != 0:
+            return self.peaks
+        for kind, name in ((0, "fp64_fma"), (1, "fp32_fma"), (2, "mufu_ex2"), (3, "f64_exp"), (4, "fp64_mma"),
+                           (16, "tf32_mma"), (17, "tcgen05_tf32")):
             v = ctypes.c_double()
             _lib.check(_lib.lib().cgp_peak_probe(kind, ctypes.byref(v)))
-            peaks[name] = v.value
+            self.peaks[name] = v.value
+        return self.peaks
 
-    collective_in_graph = False
-    if not args.no_graph:
-        # Kuf / Kdiag / Kuu of each phase on parallel graph branches; with several ranks the NCCL all-reduce of the
-        # packed gradients is captured behind them, so a data-parallel step is one graph launch
-        if world > 1 and args.graph_collective:
-            try:
-                hp.capture(overlapped=True, after=lambda: dist.all_reduce(hp.grads))
-                collective_in_graph = True
-            except Exception as exc:  # keep the collective outside the graph, say why
-                sys.stderr.write("all-reduce not captured (%s); launching it after the graph\n" % str(exc)[:200])
-                hp.graph = None
-        if hp.graph is None:
-            hp.capture(overlapped=True)
-    if world > 1:  # every rank must take the same path
-        flag = torch.tensor([1.0 if collective_in_graph else 0.0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if collective_in_graph and flag.item() < 1.0:
-            collective_in_graph = False
-            hp.capture(overlapped=True)
-    if collective_in_graph:
-        def allreduce():  # noqa: F811  (already inside hp.step())
-            pass
-    # ---- warm-up
-    for _ in range(max(args.warmup, 3)):
+    def max_over_ranks(self, values):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return list(values)
+        t = torch.tensor(list(values), dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def barrier(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+
+
+def build_hotpath(ctx, cfg, dtype_name, rank_seed, rows=None, gu_scale=1.0, collective=True):
+    """HotPath of `cfg` on this rank.  rows = (lo, hi): this rank's rows of the SAME minibatch (strong scaling);
+    None: the rank's own minibatch (weak scaling, seed 0+rank).  gu_scale: share of dL/dKuu this rank carries (Kuu is
+    replicated, so under a sharded step every rank back-propagates 1/world of it and the all-reduce restores the sum)."""
+    import torch
+    from convgp_b200 import _lib
+    from convgp_b200.hotpath import HotPath
+    dt = torch.float64 if dtype_name == "f64" else torch.float32
+    inp = make_inputs(cfg, rank_seed)
+    if rows is not None:
+        lo, hi = rows
+        inp["X"], inp["G"], inp["gd"] = inp["X"][lo:hi], inp["G"][:, lo:hi], inp["gd"][lo:hi]
+    inp["Gu"] = inp["Gu"] * gu_scale
+    tens = {k: (None if v is None else torch.tensor(np.ascontiguousarray(v), dtype=dt, device=ctx.dev))
+            for k, v in inp.items()}
+    layout = _lib.LAYOUT_PLANAR if cfg.layout == "planar" else _lib.LAYOUT_COLOUR_PATCH
+    mask = None
+    if cfg.G > 1:  # one RBF per colour channel of the colour patch: dims c::C (cifar.py:33-41)
+        mask = np.zeros((cfg.G, cfg.D), dtype=np.uint8)
+        for g in range(cfg.G):
+            mask[g, g::cfg.G] = 1
+    spec = _lib.Spec(dt, cfg.H, cfg.W, cfg.C, cfg.ph, cfg.pw, layout, _lib.OUT_SUM, cfg.G, False,
+                     cfg.layout == "colour", mask)
+    hp = HotPath(spec, tens["X"], tens["Z"], tens["W"], tens["var"], tens["ls"], tens["G"], tens["gd"], tens["Gu"],
+                 diag_add=cfg.diag_add, collective=collective and ctx.world > 1)
+    return hp, inp, tens, spec
+
+
+def time_steps(ctx, hp, steps, warmup, sample_clocks=False):
+    """W untimed steps, then K steps each bracketed by CUDA events on the launching stream with the L2 flushed in
+    between; barrier + synchronize on both sides; returns (total ms max over ranks, clocks)."""
+    import torch
+    for _ in range(max(warmup, 3)):
         hp.step()
-        allreduce()
     torch.cuda.synchronize()
-
-    # ---- timed region: K steps, device-resident inputs, CUDA events per step, L2 flushed between steps
-    sampler = ClockSampler(local_rank)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    if world > 1:
-        dist.barrier()
+    sampler = ClockSampler(ctx.local_rank) if sample_clocks else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    if sampler:
+        sampler.start()
     for a, b in ev:
-        flush_l2()
+        ctx.flush_l2()
         a.record()
         hp.step()
-        allreduce()
         b.record()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop()
+    ctx.barrier()
+    clocks = sampler.stop() if sampler else None
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    ctx.launches += hp.kernels_per_step * steps
+    return ctx.max_over_ranks([total_ms])[0], clocks
 
-    # ---- end-to-end through the public kernel-class API, host buffers in, gradients + loss out
+
+def per_kernel_ms(ctx, hp):
+    """CUDA events around each of the six launches, eager, L2 flushed (rank 0)."""
+    import torch
+    from convgp_b200 import _lib
+    L, s, st, p = _lib.lib(), hp.spec, _lib.stream_ptr, _lib.ptr
+
+    def k_kuf_fwd():
+        _lib.check(L.cgp_kuf_fwd(s.ref(), hp.N, hp.M, p(hp.X), p(hp.Z), p(hp.W), p(hp.variance), p(hp.lengthscales),
+                                 p(hp.Kuf), p(hp.ws), hp.ws_bytes, st()))
+
+    def k_kuu_fwd():
+        _lib.check(L.cgp_kuu_fwd(s.ref(), hp.M, p(hp.Z), p(hp.variance), p(hp.lengthscales), hp.diag_add,
+                                 p(hp.Kuu), st()))
+
+    def k_kuf_bwd():
+        _lib.check(L.cgp_kuf_bwd(s.ref(), hp.N, hp.M, p(hp.X), p(hp.Z), p(hp.W), p(hp.variance), p(hp.lengthscales),
+                                 p(hp.G), p(hp.dZ), p(hp.dW), p(hp.dvar), p(hp.dls), p(hp.ws), hp.ws_bytes, st()))
+
+    def k_kuu_bwd():
+        _lib.check(L.cgp_kuu_bwd(s.ref(), hp.M, p(hp.Z), p(hp.variance), p(hp.lengthscales), p(hp.Gu), p(hp.dZ),
+                                 p(hp.dvar), p(hp.dls), st()))
+
+    out = {}
+    for name, fn in (("kuf_fwd", k_kuf_fwd), ("kdiag_fwd", lambda: hp._kdiag_fwd(st())), ("kuu_fwd", k_kuu_fwd),
+                     ("kuf_bwd", k_kuf_bwd), ("kdiag_bwd", lambda: hp._kdiag_bwd(st())), ("kuu_bwd", k_kuu_bwd)):
+        ts = []
+        for i in range(13):
+            ctx.flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(a.elapsed_time(b))
+        out[name] = statistics.mean(ts)
+        ctx.launches += 13
+    return out
+
+
+def bound_fn(cfg, dtype_name, peaks):
+    """T_bound(flops, exps) of the binding pipe(s) and a description."""
+    D = cfg.D
+    if dtype_name == "f64":
+        fma_rate = max(peaks["fp64_fma"], peaks["fp64_mma"])  # DMMA and DFMA share the pipe; DMMA is the faster feed
+
+        def t_bound(fl, ex):
+            return fl / (2 * fma_rate) + ex / peaks["f64_exp"]
+        return t_bound, "fp64", ("FP64 pipe: flops/(2*max(DFMA, DMMA) rate) + exps/(library exp rate), all probed on "
+                                 "this GPU by cgp_peak_probe (MEASURED_PEAKS.json has no FP64 figure)")
+
+    # float32 runs on three pipes at once: the contraction FMAs (2D of the 2D+2G / 2D+8G flops of a pair, 4D of the
+    # 4D+8G of a Kuf backward pair) on tcgen05 tensor cores at three TF32 MMAs per float32 product, the exps on MUFU,
+    # everything else on the FP32 FMA pipe.  The slowest of the three bounds the kernel.
+    def t_bound(fl, ex):
+        pairs = ex / cfg.G
+        per_pair = fl / pairs
+        contraction = pairs * (4 * D if per_pair > 3 * D + 4 * cfg.G else 2 * D)
+        return max(3 * (contraction / 2) / peaks["tcgen05_tf32"], ex / peaks["mufu_ex2"],
+                   (fl - contraction) / (2 * peaks["fp32_fma"]))
+    return t_bound, "mufu", ("max(3 * contraction FMAs / tcgen05 kind::tf32 rate, exps / MUFU ex2 rate, remaining flops / "
+                             "(2 * FFMA rate)): the three pipes run concurrently; MUFU binds at this shape.  All rates "
+                             "probed on this GPU by cgp_peak_probe")
+
+
+def step_bound(cfg, dtype_name, peaks, n_images, executed_only=False, kd_saved=True):
+    work = algorithmic_work(cfg, n_images)
+    t_bound, _, _ = bound_fn(cfg, dtype_name, peaks)
+    names = [k for k in work if k != "step"]
+    if executed_only and kd_saved:
+        # The Kdiag backward consumes row sums its forward saved, so the library EXECUTES one sweep of the P x P
+        # Gram per step, not the two that SURVEY.md 8d's algorithmic count assumes.
+        names = [k for k in names if k != "kdiag_bwd"]
+    if dtype_name == "f64":
+        return t_bound(sum(work[k][0] for k in names), sum(work[k][1] for k in names))
+    return sum(t_bound(*work[k]) for k in names)  # each kernel has its own binding pipe
+
+
+def measure_e2e(ctx, cfg, dtype_name, hp, inp, tens, steps):
+    """The same step through the public kernel classes + torch autograd (host minibatch in, packed gradients + loss
+    out, every step; CUDA-graph replay when capturable) and straight over the C ABI (HotPath)."""
+    import torch
+    import torch.distributed as dist
     from convgp_b200 import convkernels as ck, kernels as bk
     from convgp_b200.settings import settings
+    world, dev = ctx.world, ctx.dev
+    dt = tens["X"].dtype
+    es = 8 if dtype_name == "f64" else 4
     settings.float_type = dt
     settings.device = dev
-    kern = ck.WeightedConv(bk.RBF(D), [H, W_IMG], [PH, PW]) + bk.White(1, 1e-3)
+    kern = ck.WeightedConv(bk.RBF(cfg.D), [cfg.H, cfg.W], [cfg.ph, cfg.pw]) + bk.White(1, 1e-3)
     conv = kern.kern_list[0]
     Zp = tens["Z"].clone().requires_grad_(True)
     free = [conv.W.free, conv.basekern.variance.free, conv.basekern.lengthscales.free, kern.white.variance.free, Zp]
@@ -310,8 +471,7 @@ def run_gpu(args):
         torch.cuda.current_stream().synchronize()
 
     def timed(fn, n):
-        if world > 1:
-            dist.barrier()
+        ctx.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(n):
@@ -321,15 +481,12 @@ def run_gpu(args):
 
     for _ in range(3):
         e2e_eager_step()
-    e2e_steps = max(10, min(args.steps, 100))
+    e2e_steps = max(10, min(steps, 100))
     e2e_eager_s = timed(e2e_eager_step, e2e_steps)
+    ctx.launches += 6 * (e2e_steps + 3)
 
-    # The same public-API step (kernel classes + autograd, H2D in, D2H out) captured once in a CUDA
-    # graph and replayed: the deployment pattern for a ~1 ms step, where Python dispatch of the
-    # small parameter-transform ops otherwise costs as much as the kernels.  The NCCL all-reduce
-    # stays outside the graph.
     e2e_s, e2e_mode = e2e_eager_s, "eager"
-    if not args.no_graph:
+    if not ctx.args.no_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -354,23 +511,19 @@ def run_gpu(args):
             e2e_graph_step()
             ref_out = out_host.clone()
             e2e_eager_step()
-            if not torch.allclose(ref_out, out_host, rtol=1e-6 if args.dtype == "f64" else 1e-3, atol=1e-6):
+            if not torch.allclose(ref_out, out_host, rtol=1e-6 if dtype_name == "f64" else 1e-3, atol=1e-6):
                 raise RuntimeError("graph-replayed step disagrees with the eager step")
             e2e_s, e2e_mode = timed(e2e_graph_step, e2e_steps), "cuda_graph"
+            ctx.launches += 6 * e2e_steps
         except Exception as exc:  # keep the eager number, say why
             e2e_mode = "eager (graph capture failed: %s)" % str(exc)[:120]
 
-    # ---- the same step driven straight through the C ABI (HotPath: pre-allocated buffers, the three-branch CUDA
-    # graph), still with the minibatch coming from pinned host memory and the packed gradients + Kdiag going back
-    # to host memory every step.  Reported next to the kernel-class number: the difference is torch's autograd
-    # and parameter-transform dispatch, not the library.
     out_c = torch.empty(hp.grads.numel() + hp.Kdiag.numel(), dtype=dt).pin_memory()
     ng = hp.grads.numel()
 
     def e2e_cabi_step():
         hp.X.copy_(X_host, non_blocking=True)
         hp.step()
-        allreduce()
         out_c[:ng].copy_(hp.grads, non_blocking=True)
         out_c[ng:].copy_(hp.Kdiag.reshape(-1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -378,155 +531,241 @@ def run_gpu(args):
     for _ in range(3):
         e2e_cabi_step()
     e2e_cabi_s = timed(e2e_cabi_step, e2e_steps)
+    ctx.launches += hp.kernels_per_step * (e2e_steps + 3)
+    e2e_s, e2e_eager_s, e2e_cabi_s = ctx.max_over_ranks([e2e_s, e2e_eager_s, e2e_cabi_s])
+    images = cfg.N * world
+    h2d = cfg.N * cfg.H * cfg.W * cfg.C * es
+    return {"value": images * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": n_out * es, "steps": e2e_steps, "mode": e2e_mode,
+            "eager_value": images * e2e_steps / e2e_eager_s,
+            "api": "kernel classes (Kzx / Kdiag / Kzz) + torch autograd; X from pinned host memory, packed "
+                   "gradients + loss back to host memory, every step",
+            "c_abi": {"value": images * e2e_steps / e2e_cabi_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": int(out_c.numel()) * es,
+                      "api": "HotPath.step() over the C ABI (pre-allocated buffers, one CUDA graph incl. the gradient "
+                             "all-reduce), same host-to-device and device-to-host copies every step"}}
 
-    # ---- max over ranks
-    if world > 1:
-        tt = torch.tensor([total_ms, e2e_s, e2e_eager_s, e2e_cabi_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, e2e_eager_s, e2e_cabi_s = tt.tolist()
 
-    # ---- per-kernel durations (rank 0): CUDA events around each launch, eager, L2 flushed
-    per_kernel = {}
-    if rank == 0:
-        L, s, st = _lib.lib(), spec, _lib.stream_ptr
-        p = _lib.ptr
+def _traffic(dtype_name, kernel):
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture (latest first)."""
+    try:
+        for name in ("r2_traffic.json", "r1z_traffic.json", "r1_traffic.json"):
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                v = json.load(open(path)).get(dtype_name, {}).get(kernel)
+                if v is not None:
+                    return v
+    except Exception:
+        pass
+    return None
 
-        def k_kuf_fwd():
-            _lib.check(L.cgp_kuf_fwd(s.ref(), hp.N, hp.M, p(hp.X), p(hp.Z), p(hp.W), p(hp.variance), p(hp.lengthscales),
-                                     p(hp.Kuf), None, 0, st()))
 
-        def k_kdiag_fwd():  # the forward that stores the per-image row sums its backward is made of, when covered
-            hp._kdiag_fwd(st())
-
-        def k_kuu_fwd():
-            _lib.check(L.cgp_kuu_fwd(s.ref(), hp.M, p(hp.Z), p(hp.variance), p(hp.lengthscales), hp.diag_add,
-                                     p(hp.Kuu), st()))
-
-        def k_kuf_bwd():
-            _lib.check(L.cgp_kuf_bwd(s.ref(), hp.N, hp.M, p(hp.X), p(hp.Z), p(hp.W), p(hp.variance), p(hp.lengthscales),
-                                     p(hp.G), p(hp.dZ), p(hp.dW), p(hp.dvar), p(hp.dls), None, 0, st()))
-
-        def k_kdiag_bwd():
-            hp._kdiag_bwd(st())
-
-        def k_kuu_bwd():
-            _lib.check(L.cgp_kuu_bwd(s.ref(), hp.M, p(hp.Z), p(hp.variance), p(hp.lengthscales), p(hp.Gu), p(hp.dZ),
-                                     p(hp.dvar), p(hp.dls), st()))
-
-        for name, fn in (("kuf_fwd", k_kuf_fwd), ("kdiag_fwd", k_kdiag_fwd), ("kuu_fwd", k_kuu_fwd),
-                         ("kuf_bwd", k_kuf_bwd), ("kdiag_bwd", k_kdiag_bwd), ("kuu_bwd", k_kuu_bwd)):
-            ts = []
-            for i in range(13):
-                flush_l2()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                fn()
-                b.record()
-                torch.cuda.synchronize()
-                if i >= 3:
-                    ts.append(a.elapsed_time(b))
-            per_kernel[name] = statistics.mean(ts)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline
-    work = algorithmic_work(N_BATCH)
-    if args.dtype == "f64":
-        fma_rate = max(peaks["fp64_fma"], peaks["fp64_mma"])  # DMMA and DFMA share the pipe; DMMA is the faster feed
-
-        def t_bound(fl, ex):
-            return fl / (2 * fma_rate) + ex / peaks["f64_exp"]
-        pipe, peak_note = "fp64", ("FP64 pipe: flops/(2*max(DFMA, DMMA) rate) + exps/(library exp rate), all probed on "
-                                   "this GPU by cgp_peak_probe (MEASURED_PEAKS.json has no FP64 figure)")
-    else:
-        # float32 runs on three pipes at once: the contraction FMAs (2D of the 2D+2 / 2D+8 flops of a pair, 4D of
-        # the 4D+8 of a Kuf backward pair) on tcgen05 tensor cores at three TF32 MMAs per float32 product, the exps on
-        # MUFU, everything else on the FP32 FMA pipe.  The slowest of the three bounds the kernel.
-        def t_bound(fl, ex):
-            per_pair = fl / ex
-            contraction = ex * (4 * D if per_pair > 3 * D else 2 * D)
-            return max(3 * (contraction / 2) / peaks["tcgen05_tf32"], ex / peaks["mufu_ex2"],
-                       (fl - contraction) / (2 * peaks["fp32_fma"]))
-        pipe, peak_note = "mufu", ("max(3 * contraction FMAs / tcgen05 kind::tf32 rate, exps / MUFU ex2 rate, remaining flops / "
-                                   "(2 * FFMA rate)): the three pipes run concurrently; MUFU binds at this shape.  All rates "
-                                   "probed on this GPU by cgp_peak_probe")
-    dom = max(per_kernel, key=per_kernel.get)
+def measure_headline(ctx, dtype_name, with_cpu=True):
+    """Config 3 in one dtype: weak-scaling value, per-kernel roofline, e2e.  Returns the dict of the JSON line's
+    dtype-specific fields (rank 0; other ranks get the collective parts only)."""
+    import torch  # noqa: F401
+    args, cfg = ctx.args, HEAD
+    es = 8 if dtype_name == "f64" else 4
+    hp, inp, tens, spec = build_hotpath(ctx, cfg, dtype_name, ctx.rank)
+    if not args.no_graph:
+        hp.capture(overlapped=True)
+    total_ms, clocks = time_steps(ctx, hp, args.steps, args.warmup, sample_clocks=True)
+    e2e = measure_e2e(ctx, cfg, dtype_name, hp, inp, tens, args.steps)
+    out = {"total_ms": total_ms}
+    if ctx.rank != 0:
+        return out
+    peaks = ctx.probe_peaks()
+    pk = per_kernel_ms(ctx, hp)
+    work = algorithmic_work(cfg, cfg.N)
+    t_bound, pipe, peak_note = bound_fn(cfg, dtype_name, peaks)
+    dom = max(pk, key=pk.get)
     fl, ex = work[dom]
-    if args.dtype != "f64":  # the step bound is the sum of the per-kernel bounds (each kernel has its own binding pipe)
-        step_bound = sum(t_bound(*work[k]) for k in work if k != "step")
-    dur = per_kernel[dom] * 1e-3
+    dur = pk[dom] * 1e-3
     achieved = fl / dur / 1e12
     peak = fl / t_bound(fl, ex) / 1e12
-    sfl, sex = work["step"]
     ms_per_step = total_ms / args.steps
-    step_frac = (t_bound(sfl, sex) if args.dtype == "f64" else step_bound) / (ms_per_step * 1e-3)
-    # The Kdiag backward consumes row sums its forward saved, so the library EXECUTES one sweep of the P x P Gram
-    # per step, not the two that SURVEY.md 8d's algorithmic count assumes: the same fraction on the executed work
-    # (the forward's 2D+2 flops + 1 exp per Kdiag pair taken out) is reported next to it.
-    kfl, kex = work["kdiag_fwd"]
-    step_frac_executed = ((t_bound(sfl - kfl, sex - kex) if args.dtype == "f64" else step_bound - t_bound(kfl, kex))
-                          / (ms_per_step * 1e-3)) if hp.kd_saved is not None else step_frac
+    kd_saved = hp.kd_saved is not None
+    step_frac = step_bound(cfg, dtype_name, peaks, cfg.N) / (ms_per_step * 1e-3)
+    step_frac_exec = step_bound(cfg, dtype_name, peaks, cfg.N, True, kd_saved) / (ms_per_step * 1e-3)
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    traffic = None
-    try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
-        for name in ("r1z_traffic.json", "r1_traffic.json"):  # latest capture first
-            path = os.path.join(ROOT, "profiles", name)
-            if os.path.exists(path):
-                traffic = json.load(open(path)).get(args.dtype, {}).get(dom)
-                if traffic is not None:
-                    break
-    except Exception:
-        pass
-    images = N_BATCH * world
-    value = images * args.steps / (total_ms * 1e-3)
-    e2e_value = images * e2e_steps / e2e_s
-
-    cpu_val, cores, _ = cpu_port_images_per_s(args.dtype, 40, 3)
-
-    line = {
-        "metric": "conv/wconv Kuf+Kdiag fwd+bwd images/sec (28x28, M=750)",
-        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_gpu_per_step": N_BATCH, "M": M_IND,
-                   "l2": "256 MB buffer written between timed steps (inputs are ~5 MB, far below the 126 MB L2)",
-                   "cuda_graph": not args.no_graph, "graph_branches": "Kuf | Kdiag | Kuu of each phase run on parallel branches",
-                   "collective": ("NCCL all-reduce of the packed gradient buffer per step"
-                                  + (", captured in the step's CUDA graph" if collective_in_graph else ""))
-                   if world > 1 else "none"},
+    images = cfg.N * ctx.world
+    out.update({
+        "value": images * args.steps / (total_ms * 1e-3), "ms_per_step": ms_per_step, "dtype": dtype_name,
         "roofline": {
             "bound": pipe, "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_note,
-            "kernel_ms": per_kernel, "step_frac": step_frac, "step_frac_executed_work": step_frac_executed,
-            "probes": peaks,
-            "hbm": {"algorithmic_bytes_per_step": algorithmic_bytes(N_BATCH, es),
-                    "achieved_gbs": algorithmic_bytes(N_BATCH, es) / (ms_per_step * 1e-3) / 1e9,
+            "frac": achieved / peak, "traffic": _traffic(dtype_name, dom), "peak_source": peak_note,
+            "kernel_ms": pk, "kernel_frac": {k: t_bound(*work[k]) / (pk[k] * 1e-3) for k in pk},
+            "step_frac": step_frac, "step_frac_executed_work": step_frac_exec, "probes": peaks,
+            "hbm": {"algorithmic_bytes_per_step": algorithmic_bytes(cfg, cfg.N, es),
+                    "achieved_gbs": algorithmic_bytes(cfg, cfg.N, es) / (ms_per_step * 1e-3) / 1e9,
                     "peak_gbs_measured": hbm_peak},
         },
-        "cpu_baseline": {"value": cpu_val, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "40 images of the 200-image minibatch, M=750, fwd+bwd, median of 3"},
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": N_BATCH * H * W_IMG * es,
-                "d2h_bytes_per_step": n_out * es, "steps": e2e_steps, "mode": e2e_mode,
-                "eager_value": images * e2e_steps / e2e_eager_s,
-                "api": "kernel classes (Kzx / Kdiag / Kzz) + torch autograd; X from pinned host memory, packed "
-                       "gradients + loss back to host memory, every step",
-                "c_abi": {"value": images * e2e_steps / e2e_cabi_s, "unit": "images/s",
-                          "h2d_bytes_per_step": N_BATCH * H * W_IMG * es,
-                          "d2h_bytes_per_step": int(out_c.numel()) * es,
-                          "api": "HotPath.step() over the C ABI (pre-allocated buffers, three-branch CUDA graph), "
-                                 "same host-to-device and device-to-host copies every step"}},
-        "gpu_launches": hp.kernels_per_step * args.steps,
-        "clocks": clocks,
+        "e2e": e2e, "clocks": clocks, "collective": hp.collective_name,
+    })
+    if with_cpu:
+        cpu_val, cores, _ = cpu_port_images_per_s(cfg, dtype_name, cfg.N, 2)
+        out["cpu_baseline"] = {"value": cpu_val, "unit": "images/s", "cores": cores, "kind": "port",
+                               "sample": "the full %d-image minibatch, M=%d, fwd+bwd, median of 2 after one warm-up"
+                                         % (cfg.N, cfg.M)}
+    return out
+
+
+def measure_strong(ctx, dtype_name):
+    """N > 1: the SAME 200-image minibatch split by rows over the ranks (parallel.shard_bounds), replicated
+    parameters and Kuu, the gradient all-reduce inside the step; next to it the unsharded step on one GPU (every rank
+    runs it, rank 0's gradient is the reference of grad_check)."""
+    import torch
+    from convgp_b200 import parallel
+    args, cfg = ctx.args, HEAD
+    lo, hi = parallel.shard_bounds(cfg.N, ctx.world, ctx.rank)
+    hp, _, _, _ = build_hotpath(ctx, cfg, dtype_name, 0, rows=(lo, hi), gu_scale=1.0 / ctx.world)
+    full, _, _, _ = build_hotpath(ctx, cfg, dtype_name, 0, collective=False)
+    if not args.no_graph:
+        hp.capture(overlapped=True)
+        full.capture(overlapped=True)
+    sharded_ms, _ = time_steps(ctx, hp, args.steps, args.warmup)
+    # single-GPU time of the same 200 images: rank 0's own clock (no collective, no other rank involved)
+    for _ in range(3):
+        full.step()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        ctx.flush_l2()
+        a.record()
+        full.step()
+        b.record()
+    torch.cuda.synchronize()
+    full_ms = sum(a.elapsed_time(b) for a, b in ev)
+    ctx.launches += full.kernels_per_step * args.steps
+    # gradient check: all-reduced sharded gradient against the unsharded one, per segment, relative to max |.|
+    hp.step()
+    full.step()
+    torch.cuda.synchronize()
+    worst = 0.0
+    for a, b in zip((hp.dZ, hp.dW, hp.dvar, hp.dls), (full.dZ, full.dW, full.dvar, full.dls)):
+        if a is None:
+            continue
+        den = float(b.abs().max())
+        worst = max(worst, float((a - b).abs().max()) / (den if den > 0 else 1.0))
+    worst = ctx.max_over_ranks([worst])[0]
+    ctx.barrier()
+    if ctx.rank != 0:
+        return None
+    ms, ms1 = sharded_ms / args.steps, full_ms / args.steps
+    return {"images_total": cfg.N, "rows_per_rank": [parallel.shard_bounds(cfg.N, ctx.world, r)[1]
+                                                      - parallel.shard_bounds(cfg.N, ctx.world, r)[0]
+                                                      for r in range(ctx.world)],
+            "ms_per_step": ms, "value": cfg.N / (ms * 1e-3), "unit": "images/s",
+            "ms_per_step_1gpu": ms1, "speedup_vs_1gpu": ms1 / ms, "collective": hp.collective_name,
+            "grad_check": worst, "grad_check_tol": 1e-10 if dtype_name == "f64" else 1e-4,
+            "note": "grad_check = max over [dZ|dW|dvar|dls] of max|all-reduced sharded gradient - rank 0's unsharded "
+                    "gradient| / max|unsharded|, worst rank"}
+
+
+def measure_secondary(ctx, key, dtype_name):
+    """A secondary BASELINE config: device-resident hot-path step, images/s and the step's roofline fraction.  Under
+    N > 1 the minibatch rows are sharded over the ranks (config 5: 30 rows -> 4,4,4,4,4,4,3,3 at 8)."""
+    from convgp_b200 import parallel
+    args, cfg = ctx.args, CONFIGS[key]
+    rows, gu = None, 1.0
+    if ctx.world > 1:
+        rows, gu = parallel.shard_bounds(cfg.N, ctx.world, ctx.rank), 1.0 / ctx.world
+    hp, _, _, _ = build_hotpath(ctx, cfg, dtype_name, 0, rows=rows, gu_scale=gu)
+    if not args.no_graph:
+        hp.capture(overlapped=True)
+    steps = max(20, min(args.steps, 100))
+    total_ms, _ = time_steps(ctx, hp, steps, min(args.warmup, 5))
+    if ctx.rank != 0:
+        return None
+    peaks = ctx.probe_peaks()
+    ms = total_ms / steps
+    pk = per_kernel_ms(ctx, hp) if ctx.world == 1 else None
+    kd_saved = hp.kd_saved is not None
+    out = {"workload": cfg.workload, "dtype": dtype_name, "images_per_step": cfg.N, "M": cfg.M, "ms_per_step": ms,
+           "value": cfg.N / (ms * 1e-3), "unit": "images/s",
+           "step_frac": step_bound(cfg, dtype_name, peaks, cfg.N) / (ms * 1e-3),
+           "step_frac_executed_work": step_bound(cfg, dtype_name, peaks, cfg.N, True, kd_saved) / (ms * 1e-3),
+           "families": hp.families()}
+    if pk:
+        work = algorithmic_work(cfg, cfg.N)
+        t_bound, pipe, _ = bound_fn(cfg, dtype_name, peaks)
+        out["kernel_ms"] = pk
+        out["kernel_frac"] = {k: t_bound(*work[k]) / (pk[k] * 1e-3) for k in pk}
+        out["bound"] = pipe
+    if ctx.world > 1:
+        out["rows_per_rank"] = [parallel.shard_bounds(cfg.N, ctx.world, r)[1] - parallel.shard_bounds(cfg.N, ctx.world, r)[0]
+                                for r in range(ctx.world)]
+        out["scaling"] = "strong"
+    return out
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    ctx = Ctx(args)
+    dtypes = ["f64", "f32"] if args.dtype == "both" else [args.dtype]
+    head = measure_headline(ctx, dtypes[0])
+    sub = {d: measure_headline(ctx, d, with_cpu=False) for d in dtypes[1:]}
+    strong = {}
+    if ctx.world > 1:
+        for d in dtypes:
+            strong[d] = measure_strong(ctx, d)
+    configs = {}
+    if args.secondary:
+        for key in ("cfg1", "cfg2", "cfg4", "cfg5"):
+            for d in dtypes:
+                try:
+                    configs.setdefault(key, {})[d] = measure_secondary(ctx, key, d)
+                except Exception as exc:  # a secondary line must not take the headline down; say what happened
+                    configs.setdefault(key, {})[d] = {"error": str(exc)[:300]}
+    extras = {}
+    if args.svgp_step and ctx.world == 1:
+        try:
+            from tools import svgp_step_time
+            extras["svgp_step"] = {d: svgp_step_time.measure(d, steps=20) for d in dtypes}
+        except Exception as exc:
+            extras["svgp_step"] = {"error": str(exc)[:300]}
+    if args.predict:
+        try:
+            from tools import predict_bench
+            extras["predict"] = predict_bench.measure(ctx, dtypes[0])
+        except Exception as exc:
+            extras["predict"] = {"error": str(exc)[:300]}
+
+    if ctx.rank != 0:
+        if ctx.world > 1:
+            dist.destroy_process_group()
+        return
+    cfg = HEAD
+    line = {
+        "metric": METRIC, "value": head["value"], "unit": "images/s", "n_gpus": ctx.world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
+        "config": {"workload": cfg.workload, "images_per_gpu_per_step": cfg.N, "M": cfg.M,
+                   "l2": "256 MB buffer written between timed steps (inputs are ~5 MB, far below the 126 MB L2)",
+                   "cuda_graph": not args.no_graph,
+                   "graph_branches": "Kuf | Kdiag | Kuu forward on parallel branches, JOIN, then the three backward "
+                                     "kernels on parallel branches (dL/dKuf depends on all three forwards in the ELBO)",
+                   "collective": head["collective"] if ctx.world > 1 else "none"},
+        "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"], "e2e": head["e2e"],
+        "gpu_launches": ctx.launches, "clocks": head["clocks"],
     }
+    for d, s in sub.items():
+        line[d] = {k: s[k] for k in ("value", "ms_per_step", "dtype", "roofline", "e2e", "clocks")}
+    if strong:
+        line["strong"] = strong[dtypes[0]]
+        line["grad_check"] = strong[dtypes[0]]["grad_check"]
+        for d in dtypes[1:]:
+            line[d]["strong"] = strong[d]
+            line[d]["grad_check"] = strong[d]["grad_check"]
+    if configs:
+        line["configs"] = configs
+    line.update(extras)
     emit(line)
-    if world > 1:
+    if ctx.world > 1:
         dist.destroy_process_group()
 
 
@@ -558,12 +797,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--dtype", choices=["f64", "f32"], default="f64")
+    ap.add_argument("--dtype", choices=["both", "f64", "f32"], default="both",
+                    help="both (default): float64 headline + an 'f32' sub-object with the tcgen05 path")
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--graph-collective", action="store_true",
-                    help="experimental: capture the NCCL all-reduce in the step's CUDA graph instead of launching it "
-                         "after the graph (worked at 2 GPUs in float64, hung once in float32: off by default)")
+    ap.add_argument("--secondary", action=argparse.BooleanOptionalAction, default=True,
+                    help="also time configs 1, 2, 4, 5 ('configs' sub-object)")
+    ap.add_argument("--svgp-step", action=argparse.BooleanOptionalAction, default=True,
+                    help="also time the full SVGP training step of config 3 ('svgp_step', one GPU)")
+    ap.add_argument("--predict", action=argparse.BooleanOptionalAction, default=True,
+                    help="also time the 10 000-image forward sweep ('predict'; rows sharded over the ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -19,6 +19,9 @@ EXPORTS = [
     "cgp_version", "cgp_last_error", "cgp_status_string", "cgp_geometry", "cgp_workspace_bytes", "cgp_patches",
     "cgp_kuf_fwd", "cgp_kuf_bwd", "cgp_kdiag_fwd", "cgp_kdiag_bwd", "cgp_kuu_fwd", "cgp_kuu_bwd",
     "cgp_kfull_fwd", "cgp_peak_probe", "cgp_kdiag_saved_elems", "cgp_kdiag_fwd_saved", "cgp_kdiag_bwd_saved",
+    "cgp_kernel_family", "cgp_set_option", "cgp_get_option",
+    "cgp_comm_create", "cgp_comm_handle", "cgp_comm_connect", "cgp_comm_local", "cgp_comm_result",
+    "cgp_comm_allreduce", "cgp_comm_status", "cgp_comm_destroy",
 ]
 
 
@@ -72,10 +75,29 @@ def lib():
     L.cgp_kuu_bwd.argtypes = [dp, i32] + [vp] * 7 + [vp]
     L.cgp_kfull_fwd.argtypes = [dp, i32, i32] + [vp] * 6 + [vp, sz, vp]
     L.cgp_peak_probe.argtypes = [i32, ctypes.POINTER(dbl)]
+    L.cgp_kernel_family.restype = ctypes.c_char_p
+    L.cgp_kernel_family.argtypes = [dp, i32, i32, i32]
+    L.cgp_set_option.argtypes = [ctypes.c_char_p, i32]
+    L.cgp_get_option.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32)]
+    L.cgp_comm_create.argtypes = [i32, i32, sz, ctypes.POINTER(vp)]
+    L.cgp_comm_handle.argtypes = [vp, vp]
+    L.cgp_comm_connect.argtypes = [vp, vp]
+    L.cgp_comm_local.restype = vp
+    L.cgp_comm_local.argtypes = [vp]
+    L.cgp_comm_result.restype = vp
+    L.cgp_comm_result.argtypes = [vp]
+    L.cgp_comm_allreduce.argtypes = [vp, i32, sz, vp]
+    L.cgp_comm_status.argtypes = [vp]
+    L.cgp_comm_destroy.argtypes = [vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L
     return L
+
+
+def set_option(name, value):
+    """Explicit kernel-family selection (cgp_set_option): value < 0 restores the default."""
+    check(lib().cgp_set_option(name.encode(), int(value)))
 
 
 def check(status):

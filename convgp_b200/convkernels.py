@@ -174,11 +174,13 @@ class ConvRBF(Conv):
 
 
 class WeightedConvRBF(ConvRBF):
-    """convkernels.py:228-248."""
+    """convkernels.py:228-248.  As in the reference, only ``Kzx`` is weighted: ``K`` and ``Kdiag`` are inherited
+    UNWEIGHTED from ``Conv`` (the reference class overrides nothing else), pinned by tests/test_oracle.py."""
 
     def __init__(self, img_size, patch_size):
         ConvRBF.__init__(self, img_size, patch_size)
         self.W = Param(np.ones(self.num_patches))
 
-    def _weights(self, dtype):
-        return self.W().to(dtype)
+    def Kzx(self, Z, X):  # convkernels.py:233-248
+        var, ls = self._base_params(X.dtype)
+        return ops.kuf(self._spec(X.dtype), X, Z, self.W().to(X.dtype), var, ls)

@@ -160,16 +160,23 @@ static size_t fast_smem(const FastParams<T>& p, int tpb, bool bwd) {
   return n * sizeof(T);
 }
 
-// Tuning knobs (development only; read once): CGP_KUF_FWD / CGP_KUF_BWD / CGP_KDIAG_FWD / CGP_KDIAG_BWD
-// = "mma" | "fma" select the float64 kernel family, CGP_KDIAG_WARPS caps warps per CTA.
-static int env_choice(const char* name, int dflt) {
-  const char* v = getenv(name);
-  if (!v) return dflt;
-  if (!strcmp(v, "umma")) return 2;
-  if (!strcmp(v, "mma")) return 1;
-  if (!strcmp(v, "fma")) return 0;
-  return atoi(v);
+// Kernel-family selection: explicit, through cgp_set_option (include/convgp_b200.h) -- the library reads no
+// environment variables.  -1 = default.
+struct Options {
+  int kuf_fwd = -1, kuf_bwd = -1, kdiag_fwd = -1, kdiag_bwd = -1;
+  int kuf_fwd_f32 = -1, kuf_bwd_f32 = -1, kdiag_fwd_f32 = -1, kdiag_bwd_f32 = -1;
+  int kuf_dw_pass = -1, kuf_tiles = -1, tf32_tiles = -1, kdiag_warps = -1;
+};
+static Options g_opt;
+static int* option_slot(const char* name) {
+  if (!name) return nullptr;
+#define OPT(n) if (!strcmp(name, #n)) return &g_opt.n;
+  OPT(kuf_fwd) OPT(kuf_bwd) OPT(kdiag_fwd) OPT(kdiag_bwd) OPT(kuf_fwd_f32) OPT(kuf_bwd_f32) OPT(kdiag_fwd_f32)
+  OPT(kdiag_bwd_f32) OPT(kuf_dw_pass) OPT(kuf_tiles) OPT(tf32_tiles) OPT(kdiag_warps)
+#undef OPT
+  return nullptr;
 }
+static inline int opt(int v, int dflt) { return v < 0 ? dflt : v; }
 
 template <typename T>
 static size_t mma_smem(const FastParams<T>& p, bool bwd) {
@@ -296,7 +303,7 @@ static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int
     cudaMemsetAsync(tr, 0, 64 * 24 * sizeof(long long), st);
     p.trace = tr;
     g_umma_trace = tr;
-    p.ablate = getenv("CGP_UMMA_ABLATE") ? atoi(getenv("CGP_UMMA_ABLATE")) : 0;
+    p.ablate = 0;
   }
 #endif
   const int racc_rows = std::max(g.P, (M + umma::TM - 1) / umma::TM * umma::TM);
@@ -393,7 +400,7 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
   }
   if constexpr (std::is_same<T, float>::value) {
-    static const int fam = env_choice(BWD ? "CGP_KUF_BWD_F32" : "CGP_KUF_FWD_F32", 2);  // "umma" | "mma" | "fma"
+    const int fam = opt(BWD ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 2);  // 2 umma32 | 1 hmma32 | 0 scalar
     if (fam == 2 && umma_ok(d, g, mode, M) &&
         umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total <= 227 * 1024) {
       if (!BWD) return run_umma_rowsum(0, d, g, N, M, X, Z, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st);
@@ -401,7 +408,7 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
       if (g.P > umma::TN) {
       // dW rides in the dZ kernel (column sums of the same exponentials); CGP_KUF_DW_PASS=1 selects the
       // stand-alone pass (rowsum mode 3) instead
-      static const int dw_pass = env_choice("CGP_KUF_DW_PASS", 0);
+      const int dw_pass = opt(g_opt.kuf_dw_pass, 0);
       const bool want_dw = dW && W;
       if (dZ || dvar || dls || (want_dw && !dw_pass)) {
         int rc = run_umma_dz(d, g, N, M, X, Z, W, var, ls, G, dZ, dvar, dls, st, (want_dw && !dw_pass) ? dW : nullptr);
@@ -413,10 +420,10 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
       }
     }
   }
-  static const int use_mma = env_choice(BWD ? "CGP_KUF_BWD" : "CGP_KUF_FWD", 1);
+  const int use_mma = opt(BWD ? g_opt.kuf_bwd : g_opt.kuf_fwd, 1);
   if constexpr (std::is_same<T, double>::value) if (use_mma) {
     // float64: FP64 MMA kernels, work items are blocks of kOctBlock patch octets
-    static const int nt = env_choice("CGP_KUF_TILES", 4);  // row tiles per warp (2 or 4)
+    const int nt = opt(g_opt.kuf_tiles, 4);  // row tiles per warp (2 or 4)
     const int nblk = (g.Pc + 8 * kOctBlock - 1) / (8 * kOctBlock);
     const int tpb_m = 32 * pick_warps((M + (8 * nt) - 1) / (8 * nt) * 32, 1, 4);  // a warp covers 8*nt rows
     const int rows_cta = (tpb_m / 32) * 8 * nt;
@@ -430,10 +437,10 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL
   }
-  static const int use_tc = env_choice(BWD ? "CGP_KUF_BWD_F32" : "CGP_KUF_FWD_F32", 2);  // "umma" | "mma" | "fma"
+  const int use_tc = opt(BWD ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 2);
   if constexpr (std::is_same<T, float>::value) if (use_tc) {
     // float32: 3xTF32 tensor-core kernels
-    static const int nt_env = env_choice("CGP_TF32_TILES", 0);
+    const int nt_env = opt(g_opt.tf32_tiles, 0);
     const int nt = nt_env ? nt_env : 4;  // 16-row tiles per warp
     const int nblk = (g.Pc + 8 * kOctBlock - 1) / (8 * kOctBlock);
     const int tpb_m = 32 * pick_warps((M + (16 * nt) - 1) / (16 * nt) * 32, 1, 4);
@@ -471,11 +478,11 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
   // C*P' patches of the image pair with each other (Conv with colour_channels > 1)
   p.ndom = (mode == 2 || p.out_per_channel) ? d->C : 1;
   const int ppd = d->C / p.ndom, Pd = ppd * g.Pc, Hd = ppd * g.Hout;
-  static const int use_mma = env_choice(BWD ? "CGP_KDIAG_BWD" : "CGP_KDIAG_FWD", 1);
-  static const int use_tc32 = env_choice(BWD ? "CGP_KDIAG_BWD_F32" : "CGP_KDIAG_FWD_F32", 2);
+  const int use_mma = opt(BWD ? g_opt.kdiag_bwd : g_opt.kdiag_fwd, 1);
+  const int use_tc32 = opt(BWD ? g_opt.kdiag_bwd_f32 : g_opt.kdiag_fwd_f32, 2);
   const bool mma_path = std::is_same<T, double>::value ? use_mma != 0 : use_tc32 != 0;
   // the MMA kernels hold ~200-250 registers per thread: small CTAs keep several resident per SM
-  static const int max_warps_env = env_choice("CGP_KDIAG_WARPS", 0);
+  const int max_warps_env = opt(g_opt.kdiag_warps, 0);
   const int max_warps = max_warps_env > 0 ? max_warps_env : (mma_path ? 2 : 8);
   const int tpb = 32 * pick_warps(Pd, std::min(3, max_warps), max_warps);
   const int nchunk = (Pd + tpb - 1) / tpb;
@@ -527,8 +534,8 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
 static bool kdiag_saved_ok(const cgp_kernel_desc* d, const Geo& g, int mode) {
   if (mode != 1 || d->out_mode == CGP_OUT_PER_CHANNEL) return false;
   if (d->dtype == CGP_F32)
-    return env_choice("CGP_KDIAG_FWD_F32", 2) == 2 && env_choice("CGP_KDIAG_BWD_F32", 2) == 2 && umma_ok(d, g, mode, 0);
-  return env_choice("CGP_KDIAG_FWD", 1) != 0 && env_choice("CGP_KDIAG_BWD", 1) != 0;
+    return opt(g_opt.kdiag_fwd_f32, 2) == 2 && opt(g_opt.kdiag_bwd_f32, 2) == 2 && umma_ok(d, g, mode, 0);
+  return opt(g_opt.kdiag_fwd, 1) != 0 && opt(g_opt.kdiag_bwd, 1) != 0;
 }
 
 template <typename T>
@@ -545,7 +552,7 @@ static int run_kdiag_saved_fwd(const cgp_kernel_desc* d, const Geo& g, int mode,
     p.out = (T*)out; p.save = (T*)save;
     p.ndom = 1;
     const int Pd = d->C * g.Pc;
-    static const int max_warps_env = env_choice("CGP_KDIAG_WARPS", 0);
+    const int max_warps_env = opt(g_opt.kdiag_warps, 0);
     const int max_warps = max_warps_env > 0 ? max_warps_env : 2;
     const int tpb = 32 * pick_warps(Pd, std::min(3, max_warps), max_warps);
     const int nchunk = (Pd + tpb - 1) / tpb;
@@ -700,6 +707,48 @@ const char* cgp_status_string(int s) {
     case CGP_ERR_NCCL: return "NCCL error";
     default: return "unknown status";
   }
+}
+
+int cgp_set_option(const char* name, int32_t value) {
+  int* slot = option_slot(name);
+  if (!slot) { set_error("unknown option '%s'", name ? name : "(null)"); return CGP_ERR_BAD_DESC; }
+  *slot = value < 0 ? -1 : value;
+  return CGP_OK;
+}
+
+int cgp_get_option(const char* name, int32_t* value) {
+  int* slot = option_slot(name);
+  if (!slot || !value) { set_error("unknown option '%s'", name ? name : "(null)"); return CGP_ERR_BAD_DESC; }
+  *value = *slot;
+  return CGP_OK;
+}
+
+const char* cgp_kernel_family(const cgp_kernel_desc* d, int32_t N, int32_t M, int32_t which) {
+  Geo g;
+  if (geometry(d, &g) != CGP_OK || which < 0 || which > 3) return "invalid";
+  const int mode = fast_mode(d, g);
+  if (!mode) return "generic";
+  (void)N;
+  const bool f32 = d->dtype == CGP_F32;
+  if (which < 2) {  // Kuf
+    const bool bwd = which == 1;
+    if (f32) {
+      const int fam = opt(bwd ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 2);
+      if (fam == 2 && umma_ok(d, g, mode, M) &&
+          umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total <= 227 * 1024 && (!bwd || g.P > umma::TN))
+        return "umma32";
+      return fam ? "hmma32" : "scalar";
+    }
+    return opt(bwd ? g_opt.kuf_bwd : g_opt.kuf_fwd, 1) ? "dmma64" : "scalar";
+  }
+  const bool bwd = which == 3;
+  if (kdiag_saved_ok(d, g, mode)) return f32 ? "umma32" : (bwd ? "saved-row-sums" : "dmma64");
+  if (f32) {
+    const int fam = opt(bwd ? g_opt.kdiag_bwd_f32 : g_opt.kdiag_fwd_f32, 2);
+    if (fam == 2 && umma_ok(d, g, mode, 0)) return "umma32";
+    return fam ? "hmma32" : "scalar";
+  }
+  return opt(bwd ? g_opt.kdiag_bwd : g_opt.kdiag_fwd, 1) ? "dmma64" : "scalar";
 }
 
 int cgp_geometry(const cgp_kernel_desc* d, int32_t* num_patches, int32_t* patch_len) {

@@ -8,26 +8,70 @@ from ._lib import check, ptr, stream_ptr
 
 
 def _c(t):
-    if t is not None and not t.is_cuda:
+    """Contiguous, 16-byte aligned CUDA tensor (None passes through).  Row slices of a float32 tensor with an odd
+    row length keep their storage offset under .contiguous() and can start on a 4-byte boundary; the kernels use
+    8/16-byte vector loads on X and Z, so such views are copied once here instead of failing in the C ABI."""
+    if t is None:
+        return None
+    if not t.is_cuda:
         raise _lib.CgpError(-3, "tensor is not on a CUDA device (convgp_b200 has no CPU path)")
-    return None if t is None else t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0 and t.numel() > 0:
+        t = t.clone()
+    return t
+
+
+def _numel(t):
+    return 0 if t is None else int(t.numel())
+
+
+def validate(spec, X=None, Z=None, W=None, variance=None, lengthscales=None, X2=None):
+    """Shape / dtype checks of everything that crosses the C ABI as a bare pointer (the C side sees only addresses
+    and cannot check; the reference's TF graph raises a shape error in all of these cases).  Raises ValueError /
+    TypeError -- before any launch, so a wrong argument can never become an out-of-bounds device read."""
+    dt = spec.torch_dtype
+    HWC = spec.desc.H * spec.desc.W * spec.desc.C
+    for name, t in (("X", X), ("X2", X2), ("Z", Z), ("W", W), ("variance", variance), ("lengthscales", lengthscales)):
+        if t is None:
+            continue
+        if t.dtype != dt:
+            raise TypeError("%s is %s but the kernel was built for %s (settings.float_type changed?)"
+                            % (name, t.dtype, dt))
+    for name, t in (("X", X), ("X2", X2)):
+        if t is not None and (t.dim() != 2 or t.shape[1] != HWC):
+            raise ValueError("%s must be (N, H*W*C) = (N, %d) for a %dx%dx%d image kernel, got %s"
+                             % (name, HWC, spec.desc.H, spec.desc.W, spec.desc.C, tuple(t.shape)))
+    if Z is not None and (Z.dim() != 2 or Z.shape[1] != spec.D):
+        raise ValueError("Z must be (M, patch_len) = (M, %d), got %s" % (spec.D, tuple(Z.shape)))
+    if W is not None and _numel(W) != spec.P:
+        raise ValueError("W must have num_patches = %d entries, got %s" % (spec.P, tuple(W.shape)))
+    if variance is not None and _numel(variance) != spec.n_groups:
+        raise ValueError("variance must have n_groups = %d entries, got %d" % (spec.n_groups, _numel(variance)))
+    if lengthscales is not None:
+        want = spec.n_groups * (spec.D if spec.ard else 1)
+        if _numel(lengthscales) != want:
+            raise ValueError("lengthscales must have %d entries, got %d" % (want, _numel(lengthscales)))
 
 
 def _grad_buffers(spec, Z, W, variance, lengthscales):
     """One zeroed, packed gradient buffer [dZ | dW | dvariance | dlengthscales] and its views.
     The C ABI accumulates into it, and it is what the data-parallel all-reduce sums."""
     sizes = [0 if Z is None else Z.numel(), 0 if W is None else W.numel(), variance.numel(), lengthscales.numel()]
-    buf = torch.zeros(sum(sizes), dtype=variance.dtype, device=variance.device)
-    views, o = [], 0
-    for s, ref in zip(sizes, (Z, W, variance, lengthscales)):
-        views.append(None if ref is None else buf[o:o + s].view(ref.shape))
-        o += s
+    q = 16 // variance.element_size()  # every segment starts 16-byte aligned
+    offs, o = [], 0
+    for s in sizes:
+        offs.append(o)
+        o += (s + q - 1) // q * q
+    buf = torch.zeros(max(o, q), dtype=variance.dtype, device=variance.device)
+    views = [None if ref is None else buf[o:o + s].view(ref.shape)
+             for o, s, ref in zip(offs, sizes, (Z, W, variance, lengthscales))]
     return buf, views
 
 
 class _Kuf(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec, X, Z, W, variance, lengthscales):
+        validate(spec, X=X, Z=Z, W=W, variance=variance, lengthscales=lengthscales)
         X, Z, W, variance, lengthscales = map(_c, (X, Z, W, variance, lengthscales))
         N, M = X.shape[0], Z.shape[0]
         shape = (M, N, spec.C) if spec.per_channel else (M, N)
@@ -46,7 +90,7 @@ class _Kuf(torch.autograd.Function):
         spec = ctx.spec
         N, M = X.shape[0], Z.shape[0]
         _, (dZ, dW, dvar, dls) = _grad_buffers(spec, Z, W, variance, lengthscales)
-        G = G.contiguous()
+        G = _c(G)
         with torch.cuda.device(X.device):
             ws, nb = spec.workspace(N, M, X.device)
             check(_lib.lib().cgp_kuf_bwd(spec.ref(), N, M, ptr(X), ptr(Z), ptr(W), ptr(variance), ptr(lengthscales),
@@ -62,6 +106,7 @@ class _Kdiag(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec, X, W, variance, lengthscales):
         needs_grad = any(ctx.needs_input_grad[2:5])
+        validate(spec, X=X, W=W, variance=variance, lengthscales=lengthscales)
         X, W, variance, lengthscales = map(_c, (X, W, variance, lengthscales))
         N = X.shape[0]
         shape = (N, spec.C) if spec.per_channel else (N,)
@@ -89,7 +134,7 @@ class _Kdiag(torch.autograd.Function):
         spec = ctx.spec
         N = X.shape[0]
         _, (_, dW, dvar, dls) = _grad_buffers(spec, None, W, variance, lengthscales)
-        g = g.contiguous()
+        g = _c(g)
         with torch.cuda.device(X.device):
             if ctx.has_saved:
                 check(_lib.lib().cgp_kdiag_bwd_saved(spec.ref(), N, ptr(variance), ptr(lengthscales), ptr(g),
@@ -105,6 +150,7 @@ class _Kdiag(torch.autograd.Function):
 class _Kuu(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec, Z, variance, lengthscales, diag_add):
+        validate(spec, Z=Z, variance=variance, lengthscales=lengthscales)
         Z, variance, lengthscales = map(_c, (Z, variance, lengthscales))
         M = Z.shape[0]
         out = torch.empty((M, M), dtype=Z.dtype, device=Z.device)
@@ -121,7 +167,7 @@ class _Kuu(torch.autograd.Function):
         spec = ctx.spec
         M = Z.shape[0]
         _, (dZ, _, dvar, dls) = _grad_buffers(spec, Z, None, variance, lengthscales)
-        Gu = Gu.contiguous()
+        Gu = _c(Gu)
         with torch.cuda.device(Z.device):
             check(_lib.lib().cgp_kuu_bwd(spec.ref(), M, ptr(Z), ptr(variance), ptr(lengthscales), ptr(Gu), ptr(dZ),
                                          ptr(dvar), ptr(dls), stream_ptr()))
@@ -146,6 +192,7 @@ def kuu(spec, Z, variance, lengthscales, diag_add=0.0):
 def kfull(spec, X, X2, W, variance, lengthscales):
     """K(X, X2) (forward only: the reference uses it in tests and full-GP baselines, never inside
     the SVGP objective)."""
+    validate(spec, X=X, X2=X2, W=W, variance=variance, lengthscales=lengthscales)
     X, X2, W, variance, lengthscales = map(_c, (X, X2, W, variance, lengthscales))
     N = X.shape[0]
     N2 = N if X2 is None else X2.shape[0]
@@ -160,6 +207,7 @@ def kfull(spec, X, X2, W, variance, lengthscales):
 
 def patches(spec, X):
     """_get_patches(X): (N, P, D)."""
+    validate(spec, X=X)
     X = _c(X)
     out = torch.empty((X.shape[0], spec.P, spec.D), dtype=X.dtype, device=X.device)
     with torch.cuda.device(X.device):

@@ -81,7 +81,7 @@ class Model(Parameterized):
         ``step()`` draws a fresh minibatch (the indices are copied into a static device buffer)."""
         ps = self.free_params()
         free = [p.free for p in ps]
-        self._begin_static_minibatch()
+        static_idx = self._begin_static_minibatch()  # owned by the returned step, not left on the model
 
         def body():
             f = -(self.build_likelihood() + self.build_prior())
@@ -89,19 +89,22 @@ class Model(Parameterized):
             return torch.cat([f.detach().reshape(1)] + [(g if g is not None else torch.zeros_like(t)).reshape(-1)
                                                 for g, t in zip(grads, free)])
 
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                body()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            flat = body()
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                flat = body()
+        finally:
+            self._mb_idx = None  # eager _objective / optimize / compute_log_likelihood sample fresh minibatches again
 
         def step():
-            self._next_static_minibatch()
+            self._next_static_minibatch(static_idx)
             graph.replay()
             parallel.allreduce_sum_(flat)
             return flat
@@ -110,9 +113,9 @@ class Model(Parameterized):
         return step
 
     def _begin_static_minibatch(self):
-        pass
+        return None
 
-    def _next_static_minibatch(self):
+    def _next_static_minibatch(self, static_idx):
         pass
 
     def optimize(self, method="L-BFGS-B", maxiter=1000, callback=None, lr=1e-3, **kw):
@@ -169,15 +172,31 @@ class SVGP(Model):
         return self.X[idx], self.Y[idx]
 
     def _begin_static_minibatch(self):
-        if self.minibatch_size is not None and self.minibatch_size < self.num_data:
-            self._mb_idx_host = torch.empty(self.minibatch_size, dtype=torch.long).pin_memory()
-            self._mb_idx = torch.zeros(self.minibatch_size, dtype=torch.long, device=self.X.device)
-            self._next_static_minibatch()
+        """Static device index buffer for CUDA-graph mode.  ``self._mb_idx`` points at it only while the graph is
+        being captured (``graphed_objective`` clears it afterwards); the returned state belongs to the graphed step.
+        Two pinned host buffers alternate, each guarded by an event recorded after its H2D copy, so rewriting a
+        host buffer can never race a copy that is still queued."""
+        if self.minibatch_size is None or self.minibatch_size >= self.num_data:
+            return None
+        st = {"host": [torch.empty(self.minibatch_size, dtype=torch.long).pin_memory() for _ in range(2)],
+              "event": [None, None], "turn": 0,
+              "dev": torch.zeros(self.minibatch_size, dtype=torch.long, device=self.X.device)}
+        self._mb_idx = st["dev"]
+        self._next_static_minibatch(st)
+        return st
 
-    def _next_static_minibatch(self):
-        if getattr(self, "_mb_idx", None) is not None:
-            self._mb_idx_host.copy_(torch.from_numpy(self._rng.permutation(self.num_data)[:self.minibatch_size]))
-            self._mb_idx.copy_(self._mb_idx_host, non_blocking=True)
+    def _next_static_minibatch(self, st):
+        if st is None:
+            return
+        i = st["turn"]
+        st["turn"] = 1 - i
+        if st["event"][i] is not None:
+            st["event"][i].synchronize()
+        st["host"][i].copy_(torch.from_numpy(self._rng.permutation(self.num_data)[:self.minibatch_size]))
+        st["dev"].copy_(st["host"][i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        st["event"][i] = ev
 
     # ------------------------------------------------------------------ model terms
     def build_prior_KL(self):
@@ -226,7 +245,12 @@ class SVGP(Model):
         batch costs one Kuf + Kdiag evaluation and two GEMMs.  Returns ``(mean, var)`` of y, or the log
         predictive density when ``density_Y`` is given.  Rows of ``Xnew`` are sharded over ranks when a
         process group is initialised (each rank returns its shard)."""
-        assert self.whiten and not self.q_diag, "predict_batched covers the whitened full-covariance model"
+        if type(self).build_predict is not SVGP.build_predict:
+            raise NotImplementedError("predict_batched re-uses the factors of SVGP.build_predict; %s overrides "
+                                      "build_predict -- use predict_y / predict_density in batches"
+                                      % type(self).__name__)
+        if not (self.whiten and not self.q_diag):
+            raise NotImplementedError("predict_batched covers the whitened full-covariance model")
         with torch.no_grad():
             Xnew = parallel.shard_rows(as_tensor(Xnew))
             Yd = None if density_Y is None else parallel.shard_rows(as_tensor(density_Y))

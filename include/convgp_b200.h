@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define CGP_VERSION 100 /* 0.1.0 */
+#define CGP_VERSION 200 /* 0.2.0 */
 
 enum cgp_dtype { CGP_F32 = 0, CGP_F64 = 1 };
 /* Conv._get_patches (convkernels.py:38-62): channels are separate images, D = ph*pw, P = C*P'.
@@ -51,7 +51,7 @@ enum cgp_status {
   CGP_ERR_CUDA = -4,        /* CUDA runtime error (message in cgp_last_error)      */
   CGP_ERR_WORKSPACE = -5,   /* workspace too small                                 */
   CGP_ERR_NOT_PD = -6,      /* Cholesky pivot <= 0 (index via cgp_last_error)      */
-  CGP_ERR_NCCL = -7
+  CGP_ERR_NCCL = -7         /* collective failure: peer buffer cannot be mapped / a rank never arrived */
 };
 
 typedef struct cgp_kernel_desc {
@@ -132,6 +132,38 @@ int cgp_kfull_fwd(const cgp_kernel_desc* d, int32_t N, int32_t N2, const void* X
  * 3 = this library's double-precision exp, 4 = FP64 mma.sync m8n8k4 (counted as FMAs),
  * 16 = TF32 mma.sync m16n8k8, 17 = tcgen05.mma kind::tf32 (FMAs per second). */
 int cgp_peak_probe(int32_t kind, double* ops_per_s);
+
+/* Which hand-written CUDA kernel family a launch of this configuration dispatches to -- "dmma64" (FP64 warp MMA),
+ * "umma32" (tcgen05 + TMEM), "hmma32" (mma.sync 3xTF32), "scalar", "generic" -- for which = 0 Kuf forward,
+ * 1 Kuf backward, 2 Kdiag forward, 3 Kdiag backward.  Static string; "invalid" for a bad descriptor. */
+const char* cgp_kernel_family(const cgp_kernel_desc* d, int32_t N, int32_t M, int32_t which);
+
+/* Explicit kernel-family selection (all families are CUDA; there is no CPU path to select).  name: "kuf_fwd",
+ * "kuf_bwd", "kdiag_fwd", "kdiag_bwd" (float64 families: 1 = dmma64, 0 = scalar) and the same with the suffix
+ * "_f32" (2 = umma32, 1 = hmma32, 0 = scalar); "kuf_dw_pass" (1 = dW of Kuf from the stand-alone row-sum pass).
+ * value < 0 restores the default.  Process-wide; used by the variant tests and the profiling tools. */
+int cgp_set_option(const char* name, int32_t value);
+int cgp_get_option(const char* name, int32_t* value);
+
+/* ---- data-parallel gradient exchange: one-shot peer-memory all-reduce -------------------------
+ * One process per GPU.  cgp_comm_create allocates this rank's segment (the buffer the backward kernels accumulate
+ * into, cgp_comm_local, and a local result buffer, cgp_comm_result); cgp_comm_handle exports its 64-byte CUDA IPC
+ * handle; the caller exchanges the handles (torch.distributed / MPI / files -- plumbing) and passes all `world` of
+ * them, in rank order, to cgp_comm_connect, which maps every peer's segment over NVLink.  cgp_comm_allreduce then
+ * enqueues ONE kernel on `stream` that sums the first n_elems elements of every rank's local buffer into this
+ * rank's result buffer (rank order: bit-identical on all ranks), bracketed by ready / done flag rounds so the local
+ * buffer may be overwritten as soon as the kernel has finished.  Capturable in a CUDA graph (the epoch lives in
+ * device memory).  Every rank must enqueue the same sequence of calls.  Replaces nothing in the reference (it is
+ * single-device); it is the collective of the row-sharded step. */
+typedef struct cgp_comm cgp_comm;
+int cgp_comm_create(int32_t world, int32_t rank, size_t bytes, cgp_comm** out);
+int cgp_comm_handle(cgp_comm* c, void* handle64);
+int cgp_comm_connect(cgp_comm* c, const void* handles);
+void* cgp_comm_local(cgp_comm* c);
+void* cgp_comm_result(cgp_comm* c);
+int cgp_comm_allreduce(cgp_comm* c, int32_t dtype, size_t n_elems, void* stream);
+int cgp_comm_status(cgp_comm* c); /* CGP_ERR_NCCL if a flag poll timed out; synchronises the device */
+int cgp_comm_destroy(cgp_comm* c);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,20 @@ def varexp_multiclass(Fmu, Fvar, Y, num_classes, epsilon=1e-3):
     return p * np.log(1 - epsilon) + (1.0 - p) * np.log(epsilon / (num_classes - 1.0))
 
 
+def predict_y_multiclass(Fmu, Fvar, num_classes, epsilon=1e-3):
+    """GPflow 0.x MultiClass.predict_mean_and_var with RobustMax: per class c the probability that latent c is the
+    largest, mixed with epsilon; variance of the one-hot indicator."""
+    ps = np.concatenate([prob_is_largest(np.full((Fmu.shape[0],), c), Fmu, Fvar, num_classes)
+                         for c in range(num_classes)], axis=1)
+    mu = ps * (1 - epsilon) + (1.0 - ps) * (epsilon / (num_classes - 1.0))
+    return mu, mu - mu ** 2
+
+
+def predict_density_multiclass(Fmu, Fvar, Y, num_classes, epsilon=1e-3):
+    p = prob_is_largest(Y, Fmu, Fvar, num_classes)
+    return np.log(p * (1 - epsilon) + (1.0 - p) * (epsilon / (num_classes - 1.0)))
+
+
 def svgp_predict(kern, Z, X, q_mu, q_sqrt, whiten=True, jitter=1e-5):
     Kmm = kern.Kzz(Z) + jitter * np.eye(Z.shape[0])
     return O.conditional(kern.Kdiag(X), kern.Kzx(Z, X), Kmm, q_mu, q_sqrt, whiten)

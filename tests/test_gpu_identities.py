@@ -35,6 +35,21 @@ def test_T1_convrbf():
     assert np.allclose(wkr.compute_Kzx(Z, X), okr.Kzx(Z, X))
 
 
+def test_weighted_convrbf_weights_only_kzx():
+    """convkernels.py:228-248: WeightedConvRBF overrides only Kzx; K and Kdiag are Conv's, unweighted."""
+    ckernels, GP, _ = _k()
+    from oracle import convgp_oracle as O
+    w = np.random.RandomState(3).randn(4)
+    X = np.random.RandomState(4).randn(3, 9)
+    wkr, kr = ckernels.WeightedConvRBF([3, 3], [2, 2]), ckernels.ConvRBF([3, 3], [2, 2])
+    okr = O.WeightedConvRBF([3, 3], [2, 2])
+    wkr.W = w
+    okr.W = w
+    assert np.allclose(wkr.compute_Kdiag(X), okr.Kdiag(X), rtol=1e-10, atol=0)
+    assert np.allclose(wkr.compute_K_symm(X), okr.K(X), rtol=1e-10, atol=0)
+    assert np.array_equal(wkr.compute_Kdiag(X), kr.compute_Kdiag(X))
+
+
 def _general():
     ckernels, GP, misvgp = _k()
     return [ckernels.Conv(GP.RBF(4), [3, 3], [2, 2]), ckernels.WeightedConv(GP.RBF(4), [3, 3], [2, 2]),

@@ -197,7 +197,7 @@ def test_graphed_objective_matches_eager_and_non_pd_raises():
     step = m.graphed_objective()
     m._rng = np.random.RandomState(12)
     flat = step().double().cpu().numpy()
-    m._mb_idx = None  # back to eager minibatching with the same random stream
+    assert m._mb_idx is None  # the static index buffer belongs to the graphed step; eager calls sample again
     m._rng = np.random.RandomState(12)
     f, g = m._objective(x0)
     assert abs(flat[0] - f) < 1e-9 * abs(f)
@@ -214,17 +214,33 @@ def test_graphed_objective_matches_eager_and_non_pd_raises():
     assert e.value.status == -6
 
 
-def test_predict_batched_matches_predict_y():
+def test_predict_batched_against_oracle():
+    """The large-N forward sweep (one Cholesky for the whole sweep, batches of rows) against the NumPy SVGP oracle
+    evaluated in one piece, and against the package's own unbatched predict_y / predict_density."""
     ck, bk, lik, _, svgp, _, _ = _pkg()
     rng = np.random.RandomState(8)
     N, M, L = 37, 9, 3
     X, Y = _data(rng, N, 100, classes=L)
     k = ck.WeightedConv(bk.RBF(9, variance=0.8, lengthscales=1.4), [10, 10], [3, 3]) + bk.White(1, 1e-3)
-    Z = O.WeightedConv(O.RBF(9, 0.8, 1.4), [10, 10], [3, 3]).init_inducing(X, M, rng=rng)
+    conv = k.kern_list[0]
+    conv.W = rng.rand(conv.num_patches) + 0.5
+    ok = O.Add([O.WeightedConv(O.RBF(9, 0.8, 1.4), [10, 10], [3, 3]), O.White(1, 1e-3)])
+    ok.kern_list[0].W = conv.W.value
+    Z = ok.kern_list[0].init_inducing(X, M, rng=rng)
     m = svgp.SVGP(X, Y, k, lik.MultiClass(L), Z, num_latent=L)
-    m.q_mu, m.q_sqrt = _variational(rng, M, L)
-    py, pv = m.predict_y(X)
+    q_mu, q_sqrt = _variational(rng, M, L)
+    m.q_mu, m.q_sqrt = q_mu, q_sqrt
+    omu, ovar = SO.svgp_predict(ok, Z, X, q_mu, q_sqrt)
+    oy, ov = SO.predict_y_multiclass(omu, ovar, L)
     by, bv = m.predict_batched(X, batch_size=10)
-    assert rel_err(by, py) < 1e-10 and rel_err(bv, pv) < 1e-10
+    assert rel_err(by, oy) < 1e-7 and rel_err(bv, ov) < 1e-7
     dens = m.predict_batched(X, batch_size=16, density_Y=Y)
+    assert rel_err(dens, SO.predict_density_multiclass(omu, ovar, Y, L)) < 1e-7
+    py, pv = m.predict_y(X)
+    assert rel_err(by, py) < 1e-10 and rel_err(bv, pv) < 1e-10
     assert rel_err(dens, m.predict_density(X, Y)) < 1e-10
+    # subclasses that override build_predict must not inherit the sweep (it would silently use the wrong kernel)
+    from convgp_b200 import svconvgp
+    m2 = svconvgp.SVConvGP(X[:, :64], Y, bk.RBF(9), lik.Gaussian(0.1), 3, 3, img_size=(8, 8))
+    with pytest.raises(NotImplementedError):
+        m2.predict_batched(X[:, :64])

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert sorted(_lib.EXPORTS) == names
-    assert L.cgp_version() == 100
+    assert L.cgp_version() == 200
 
 
 def test_descriptor_validation_without_gpu():
@@ -115,3 +115,55 @@ def test_shard_bounds_cover_all_rows():
         sizes = [hi - lo for lo, hi in got]
         assert max(sizes) - min(sizes) <= 1
     assert [hi - lo for lo, hi in (shard_bounds(30, 8, r) for r in range(8))] == [4, 4, 4, 4, 4, 4, 3, 3]
+
+
+def test_argument_validation_raises_before_any_launch():
+    """ops.validate: everything that crosses the C ABI as a bare pointer is shape- and dtype-checked on the host
+    (the reference's TF graph raises a shape error in these cases); no GPU needed to see the error."""
+    from convgp_b200 import _lib, ops
+    s = _lib.Spec(torch.float64, 28, 28, 1, 5, 5, 0, 0, 1, False, False)
+    X, Z, W = torch.zeros(3, 784, dtype=torch.float64), torch.zeros(4, 25, dtype=torch.float64), torch.ones(576, dtype=torch.float64)
+    v, l = torch.ones(1, dtype=torch.float64), torch.ones(1, dtype=torch.float64)
+    ops.validate(s, X=X, Z=Z, W=W, variance=v, lengthscales=l)
+    with pytest.raises(ValueError, match="H\\*W\\*C"):   # CIFAR-sized rows into a 28x28x1 kernel
+        ops.validate(s, X=torch.zeros(3, 3072, dtype=torch.float64))
+    with pytest.raises(ValueError, match="patch_len"):
+        ops.validate(s, Z=torch.zeros(4, 9, dtype=torch.float64))
+    with pytest.raises(ValueError, match="num_patches"):
+        ops.validate(s, W=torch.ones(100, dtype=torch.float64))
+    with pytest.raises(TypeError, match="float_type"):
+        ops.validate(s, X=X.float())
+    with pytest.raises(ValueError, match="variance"):
+        ops.validate(s, variance=torch.ones(3, dtype=torch.float64))
+    with pytest.raises(ValueError, match="lengthscales"):
+        ops.validate(s, lengthscales=torch.ones(25, dtype=torch.float64))
+    # through the public class: a wrong-length W assigned to the Param is caught at the call, not in the kernel
+    from convgp_b200 import convkernels as ck, kernels as bk
+    k = ck.WeightedConv(bk.RBF(25), [28, 28], [5, 5])
+    k.W = np.ones(7)
+    with pytest.raises(ValueError, match="num_patches"):
+        k.Kzx(Z.to(k.W().device), X.to(k.W().device))
+
+
+def test_options_api_and_family_query():
+    from convgp_b200 import _lib
+    L = _lib.lib()
+    f64 = _lib.Spec(torch.float64, 28, 28, 1, 5, 5, 0, 0, 1, False, False)
+    f32 = _lib.Spec(torch.float32, 28, 28, 1, 5, 5, 0, 0, 1, False, False)
+    gen = _lib.Spec(torch.float64, 28, 28, 1, 4, 4, 0, 0, 1, False, False)
+    assert L.cgp_kernel_family(f64.ref(), 200, 750, 0) == b"dmma64"
+    assert L.cgp_kernel_family(f32.ref(), 200, 750, 0) == b"umma32"
+    assert L.cgp_kernel_family(f32.ref(), 200, 750, 1) == b"umma32"
+    assert L.cgp_kernel_family(gen.ref(), 200, 750, 2) == b"generic"
+    _lib.set_option("kuf_fwd", 0)
+    try:
+        assert L.cgp_kernel_family(f64.ref(), 200, 750, 0) == b"scalar"
+    finally:
+        _lib.set_option("kuf_fwd", -1)
+    assert L.cgp_kernel_family(f64.ref(), 200, 750, 0) == b"dmma64"
+    assert L.cgp_set_option(b"no_such_option", 1) == -1
+
+
+def test_library_reads_no_environment():
+    src = open(os.path.join(ROOT, "convgp_b200", "csrc", "api.cu")).read()
+    assert "getenv" not in src

@@ -5,7 +5,7 @@ from convgp_b200 import _lib
 from convgp_b200.hotpath import HotPath
 dt = torch.float64 if (len(sys.argv) < 2 or sys.argv[1] == "f64") else torch.float32
 dev = torch.device("cuda", 0)
-inp = bench.make_inputs(0)
+inp = bench.make_inputs(bench.HEAD, 0)
 t = {k: torch.tensor(v, dtype=dt, device=dev) for k, v in inp.items()}
 spec = _lib.Spec(dt, 28, 28, 1, 5, 5, 0, 0, 1, False, False)
 for ov in (False, True):

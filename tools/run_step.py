@@ -16,7 +16,7 @@ ap.add_argument("--steps", type=int, default=2)
 a = ap.parse_args()
 dt = torch.float64 if a.dtype == "f64" else torch.float32
 dev = torch.device("cuda", 0)
-inp = bench.make_inputs(0)
+inp = bench.make_inputs(bench.HEAD, 0)
 t = {k: torch.tensor(v, dtype=dt, device=dev) for k, v in inp.items()}
 spec = _lib.Spec(dt, 28, 28, 1, 5, 5, 0, 0, 1, False, False)
 hp = HotPath(spec, t["X"], t["Z"], t["W"], t["var"], t["ls"], t["G"], t["gd"], t["Gu"], diag_add=1e-3 + 1e-5)
