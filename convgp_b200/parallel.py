@@ -92,7 +92,9 @@ class GradAllReduce:
         self._comm = None
         self.capturable = True
         self.name = "none"
-        if self.world > 1 and self.device.type == "cuda":
+        # the peer kernel needs one GPU per rank (its flag polls assume the peers' kernels run concurrently): NCCL
+        # groups guarantee that; under gloo several ranks may share a device
+        if self.world > 1 and self.device.type == "cuda" and dist.get_backend(group) == "nccl":
             try:
                 self._connect(_lib)
                 self.name = "one-shot peer-memory all-reduce kernel (cgp_comm_allreduce: NVLink loads of every rank's " \

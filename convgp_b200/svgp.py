@@ -68,7 +68,8 @@ class Model(Parameterized):
         f.backward()
         flat = torch.cat([f.detach().reshape(1)] + [
             (p.free.grad if p.free.grad is not None else torch.zeros_like(p.free)).reshape(-1) for p in ps])
-        parallel.allreduce_sum_(flat)
+        if getattr(self, "data_parallel", True):
+            parallel.allreduce_sum_(flat)
         out = flat.double().cpu().numpy()
         return out[0], out[1:]
 
@@ -106,7 +107,8 @@ class Model(Parameterized):
         def step():
             self._next_static_minibatch(static_idx)
             graph.replay()
-            parallel.allreduce_sum_(flat)
+            if getattr(self, "data_parallel", True):
+                parallel.allreduce_sum_(flat)
             return flat
 
         step.graph = graph
@@ -218,8 +220,9 @@ class SVGP(Model):
 
     def build_likelihood(self):  # svconvgp.py:91-104
         Xb, Yb = self._minibatch()
-        world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
-        rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        dp = torch.distributed.is_initialized() and getattr(self, "data_parallel", True)
+        world = torch.distributed.get_world_size() if dp else 1
+        rank = torch.distributed.get_rank() if dp else 0
         if world > 1:  # data parallel: this rank's rows; the KL term is counted once (rank 0)
             Xb, Yb = parallel.shard_rows(Xb, world, rank), parallel.shard_rows(Yb, world, rank)
         n_batch = self.minibatch_size if (self.minibatch_size and self.minibatch_size < self.num_data) \
