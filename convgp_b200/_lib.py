@@ -22,6 +22,7 @@ EXPORTS = [
     "cgp_kernel_family", "cgp_set_option", "cgp_get_option",
     "cgp_comm_create", "cgp_comm_handle", "cgp_comm_connect", "cgp_comm_local", "cgp_comm_result",
     "cgp_comm_allreduce", "cgp_comm_status", "cgp_comm_destroy",
+    "cgp_gemm", "cgp_potrf_inv_workspace", "cgp_potrf_inv", "cgp_potrf_check", "cgp_project_fwd", "cgp_project_bwd",
 ]
 
 
@@ -37,6 +38,17 @@ class KernelDesc(ctypes.Structure):
         ("ph", ctypes.c_int32), ("pw", ctypes.c_int32), ("layout", ctypes.c_int32), ("out_mode", ctypes.c_int32),
         ("n_groups", ctypes.c_int32), ("ard", ctypes.c_int32), ("round_x_f32", ctypes.c_int32),
         ("reserved", ctypes.c_int32), ("active", ctypes.c_void_p),
+    ]
+
+
+class GemmDesc(ctypes.Structure):
+    _fields_ = [
+        ("dtype", ctypes.c_int32), ("m", ctypes.c_int32), ("n", ctypes.c_int32), ("k", ctypes.c_int32),
+        ("trans_a", ctypes.c_int32), ("trans_b", ctypes.c_int32), ("a_tri", ctypes.c_int32), ("b_tri", ctypes.c_int32),
+        ("c_mode", ctypes.c_int32), ("accumulate", ctypes.c_int32), ("batch", ctypes.c_int32),
+        ("batch_reduce", ctypes.c_int32), ("lda", ctypes.c_int64), ("ldb", ctypes.c_int64), ("ldc", ctypes.c_int64),
+        ("stride_a", ctypes.c_int64), ("stride_b", ctypes.c_int64), ("stride_c", ctypes.c_int64),
+        ("alpha", ctypes.c_double),
     ]
 
 
@@ -89,6 +101,14 @@ def lib():
     L.cgp_comm_allreduce.argtypes = [vp, i32, sz, vp]
     L.cgp_comm_status.argtypes = [vp]
     L.cgp_comm_destroy.argtypes = [vp]
+    i64 = ctypes.c_int64
+    L.cgp_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp, vp, vp, vp]
+    L.cgp_potrf_inv_workspace.restype = sz
+    L.cgp_potrf_inv_workspace.argtypes = [i32, i32]
+    L.cgp_potrf_inv.argtypes = [i32, i32, vp, i64, vp, i64, vp, sz, vp, vp]
+    L.cgp_potrf_check.argtypes = [vp, vp]
+    L.cgp_project_fwd.argtypes = [i32] * 6 + [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    L.cgp_project_bwd.argtypes = [i32] * 5 + [vp, vp, vp, vp, i64] + [vp] * 9 + [vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

@@ -1,62 +1,49 @@
-"""The whitened, full-covariance inter-domain conditional (misvgp.py:83-165 with ``whiten=True`` and a
-3-D ``q_sqrt`` -- the case every reference script runs) as ONE autograd node with hand-derived
-gradients, written so that everything after the Cholesky is a (batched) GEMM:
+"""The inter-domain conditional from evaluated kernel matrices (misvgp.py:83-165), all six (whiten, q_sqrt rank)
+combinations, as two autograd nodes whose forward and reverse passes run entirely in the CUDA library
+(``linalg.chol_solve``: hand-written Cholesky + triangular inverse + structured GEMMs; ``linalg.project``: the fused
+variational projection):
 
-    Lm = chol(Kmm)          Li = Lm^-1 (one triangular solve against I)      A = Li Kmn
-    fmean = A^T q_mu        LTA_l = Lq_l^T A        fvar = Kdiag - colsum(A^2) + sum_m LTA^2
+    Lm = chol(Kmm)  :128        A = Lm^-1 Kmn  :131        fvar = Kdiag - colsum(A^2)  :138-140
+    not whitened: A <- Lm^-T A  :143-144                   fmean = A^T f  :147
+    q_sqrt (M, L): LTA = A * q_sqrt[:, l]  :150-151        q_sqrt (M, M, L): LTA_l = tril(q_sqrt_l)^T A  :152-155
+    fvar += colsum(LTA^2)  :162                            returns fmean (N, L), fvar (N, L)  :163-165
 
-Reverse mode re-uses Li instead of issuing triangular solves (autograd through
-``solve_triangular`` / ``cholesky`` launches dozens of small TRSM kernels per step; measured 3.4 ms
-of GPU time per config-3 step against ~1.1 ms for the patch kernels):
-
-    dLTA_l = 2 LTA_l * dfvar_l       dLq_l = tril(A dLTA_l^T)       dq_mu = A dfmean
-    dA   = sum_l Lq_l dLTA_l + q_mu dfmean^T - 2 A * dKdiag         dKmn = Li^T dA
-    dLm  = -tril(Li^T (dA A^T))      phi = tril(Lm^T dLm), diag/2   dKmm = sym(Li^T phi Li)
-
-Cholesky, the triangular inverse and the GEMMs are library calls (cuSOLVER / cuBLAS via torch); the
-hand-written CUDA of this repo is the kernel evaluation that feeds this node."""
+``shared`` variants take several right-hand sides against ONE factorisation of Kmm (the channels of
+MultiOutputInducingSVGP / SVColourConvGP, which the reference re-factorises per channel)."""
 import torch
 
-from . import _lib
-from .settings import settings
+from . import linalg
 
 
-class _WhitenedConditional(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, Kdiag, Kmn, Kmm, q_mu, q_sqrt):
-        M = Kmm.shape[0]
-        Lm, info = torch.linalg.cholesky_ex(Kmm)
-        if settings.check_cholesky and not torch.cuda.is_current_stream_capturing():
-            bad = int(info)  # TF raises on a non-PD Cholesky; so do we, with the pivot index
-            if bad != 0:
-                raise _lib.CgpError(-6, "Kmm is not positive definite (leading minor of order %d)" % bad)
-        Li = torch.linalg.solve_triangular(Lm, torch.eye(M, dtype=Kmm.dtype, device=Kmm.device), upper=False)
-        A = Li @ Kmn                                   # (M, N)
-        Lq = torch.tril(q_sqrt.permute(2, 0, 1))       # (L, M, M)
-        LTA = Lq.transpose(1, 2) @ A                   # (L, M, N)
-        fmean = A.T @ q_mu                             # (N, L)
-        fvar = (Kdiag - (A * A).sum(0))[None, :] + (LTA * LTA).sum(1)   # (L, N)
-        ctx.save_for_backward(Lm, Li, A, Lq, LTA, q_mu)
-        return fmean, fvar.T.contiguous()
+def conditional_from_factors(Kdiag, A, A2, f, q_sqrt, whiten):
+    """fmean, fvar from A = Lm^-1 Kmn (and A2 = Lm^-T A when not whitened)."""
+    if whiten:
+        return linalg.project(A, f, q_sqrt, Kdiag)
+    return linalg.project(A2, f, q_sqrt, Kdiag, A_var=A)
 
-    @staticmethod
-    def backward(ctx, dfmean, dfvar):
-        Lm, Li, A, Lq, LTA, q_mu = ctx.saved_tensors
-        dfvar_t = dfvar.T                              # (L, N)
-        dKdiag = dfvar_t.sum(0)                        # (N,)
-        dLTA = 2.0 * LTA * dfvar_t[:, None, :]         # (L, M, N)
-        dLq = torch.tril(A[None] @ dLTA.transpose(1, 2))          # (L, M, M)
-        dA = (Lq @ dLTA).sum(0) + q_mu @ dfmean.T - 2.0 * A * dKdiag[None, :]
-        dq_mu = A @ dfmean
-        dKmn = Li.T @ dA
-        dLm = -torch.tril(Li.T @ (dA @ A.T))
-        phi = torch.tril(Lm.T @ dLm)
-        phi.diagonal().mul_(0.5)
-        gK = Li.T @ phi @ Li
-        dKmm = 0.5 * (gK + gK.T)
-        return dKdiag, dKmn, dKmm, dq_mu, dLq.permute(1, 2, 0)
+
+def conditional(Kdiag, Kmn, Kmm, f, q_sqrt=None, whiten=False):
+    """misvgp.py:83-165 without the unused Xnew / X arguments: fmean (N, L), fvar (N, L)."""
+    A, A2, _ = linalg.chol_solve(Kmm, Kmn, both=not whiten)
+    return conditional_from_factors(Kdiag, A, A2, f, q_sqrt, whiten)
+
+
+def conditional_shared(Kdiag, Kmn, Kmm, f, q_sqrt, whiten, weights=None):
+    """Sum over C components that share Kmm: Kdiag (N, C), Kmn (M, N, C), f (M, L, C), q_sqrt (M, M, L, C) or
+    (M, L, C) or None.  ``weights`` (C,) scales each component's mean AND variance (SVColourConvGP's wc,
+    svconvgp.py:54-63).  One Cholesky / inverse for all components (misvgp.py:187-210 factorises C times)."""
+    C = Kmn.shape[2]
+    A, A2, _ = linalg.chol_solve(Kmm, Kmn.permute(2, 0, 1).contiguous(), both=not whiten)
+    mu, var = 0, 0
+    for c in range(C):
+        q = None if q_sqrt is None else q_sqrt[..., c]
+        fm, fv = conditional_from_factors(Kdiag[:, c], A[c], A2[c] if not whiten else None, f[:, :, c], q, whiten)
+        if weights is not None:
+            fm, fv = fm * weights[c], fv * weights[c]
+        mu, var = mu + fm, var + fv
+    return mu, var
 
 
 def whitened_conditional(Kdiag, Kmn, Kmm, q_mu, q_sqrt):
     """fmean (N, L), fvar (N, L) for whiten=True, q_sqrt (M, M, L) lower-triangular stack."""
-    return _WhitenedConditional.apply(Kdiag, Kmn, Kmm, q_mu, q_sqrt)
+    return conditional(Kdiag, Kmn, Kmm, q_mu, q_sqrt, whiten=True)

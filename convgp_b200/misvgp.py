@@ -34,31 +34,16 @@ class WeightedMultiChannelConvGP(Conv):
 
 def conditional(Xnew, X, Kdiag, Kmn, Kmm, f, full_cov=False, q_sqrt=None, whiten=False):
     """misvgp.py:83-165: GP conditional from evaluated ``Kdiag (N)``, ``Kmn (M, N)``, ``Kmm (M, M)``.
-    Returns ``fmean (N, L)``, ``fvar (N, L)``.  ``Xnew`` / ``X`` are kept for signature parity only."""
+    Returns ``fmean (N, L)``, ``fvar (N, L)``.  ``Xnew`` / ``X`` are kept for signature parity only.  All
+    arithmetic (Cholesky, triangular inverse, GEMMs, the projection and their reverse mode) runs in the CUDA library
+    (convgp_b200/conditional.py -> csrc/linalg.cu)."""
     if full_cov:
         raise NotImplementedError("full_cov needs K(Xnew, Xnew), which this entry point is not given "
                                   "(the reference's own branch is `None - A^T A`, misvgp.py:135)")
-    if whiten and q_sqrt is not None and q_sqrt.dim() == 3 and Kmn.is_cuda:
-        from .conditional import whitened_conditional  # the case every script runs: one fused autograd node
-        return whitened_conditional(Kdiag, Kmn, Kmm, f, q_sqrt)
-    num_func = f.shape[1]
-    Lm = torch.linalg.cholesky(Kmm)  # :128
-    A = torch.linalg.solve_triangular(Lm, Kmn, upper=False)  # :131
-    fvar = Kdiag - (A * A).sum(0)  # :138
-    fvar = fvar[None, :].expand(num_func, -1)  # :140
-    if not whiten:  # :143-144
-        A = torch.linalg.solve_triangular(Lm.T, A, upper=True)
-    fmean = A.T @ f  # :147
-    if q_sqrt is not None:
-        if q_sqrt.dim() == 2:  # :150-151
-            LTA = A[None, :, :] * q_sqrt.T[:, :, None]
-        elif q_sqrt.dim() == 3:  # :152-155
-            Lq = torch.tril(q_sqrt.permute(2, 0, 1))
-            LTA = Lq.transpose(1, 2) @ A[None, :, :]
-        else:
-            raise ValueError("Bad dimension for q_sqrt: %s" % str(q_sqrt.dim()))
-        fvar = fvar + (LTA * LTA).sum(1)  # :162
-    return fmean, fvar.T  # :163-165
+    if q_sqrt is not None and q_sqrt.dim() not in (2, 3):
+        raise ValueError("Bad dimension for q_sqrt: %s" % str(q_sqrt.dim()))  # misvgp.py:156-157
+    from .conditional import conditional as _cond
+    return _cond(Kdiag, Kmn, Kmm, f, q_sqrt=q_sqrt, whiten=whiten)
 
 
 def _svgp_base():
@@ -68,7 +53,7 @@ def _svgp_base():
 
 class MultiOutputInducingSVGP(_svgp_base()):
     """misvgp.py:168-210: every inducing patch carries ``kern.inducing_outputs`` (= C) inducing
-    outputs; the prediction sums the C per-channel conditionals, which share one Kmm / Cholesky.
+    outputs; the prediction sums the C per-channel conditionals, which share one Kmm and ONE Cholesky.
     (The reference re-emits Kdiag / Kmn / Kmm per channel and leaves a debug ``tf.Print`` in the
     graph, misvgp.py:194-196,209; both are dropped -- values are identical.)"""
 
@@ -90,9 +75,7 @@ class MultiOutputInducingSVGP(_svgp_base()):
         Z = self.Z()
         Kdiag, Kmn = self.kern.Kdiag(Xnew), self.kern.Kzx(Z, Xnew)
         Kmm = self.kern.Kzz(Z) + torch.eye(M, dtype=Z.dtype, device=Z.device) * settings.jitter_level
-        mu, var = 0, 0
-        for i in range(C):
-            fmu, fvar = conditional(Xnew, Z, Kdiag[:, i], Kmn[:, :, i], Kmm, q_mu[:, :, i],
-                                    q_sqrt=q_sqrt[:, :, :, i], full_cov=full_cov, whiten=self.whiten)
-            mu, var = mu + fmu, var + fvar
-        return mu, var
+        if full_cov:
+            raise NotImplementedError("full_cov")
+        from .conditional import conditional_shared  # the C channel conditionals share ONE factorisation of Kmm
+        return conditional_shared(Kdiag, Kmn, Kmm, q_mu, q_sqrt, self.whiten)

@@ -32,7 +32,9 @@ class Positive:
 
 class LowerTriangular:
     """GPflow 0.x ``transforms.LowerTriangular``: the free state holds only the lower triangles of
-    the (M, M, L) stack (svsumgp.py:41-42)."""
+    the (M, M, L) stack (svsumgp.py:41-42), in the reference's order (row, column, latent).  The constrained value is
+    STORED as L row-major (M, M) matrices -- the layout the projection kernels read -- and handed out as the
+    (M, M, L) view of that storage, so the reference's shape is kept and no transposition is ever materialised."""
 
     def __init__(self, M, L):
         self.M, self.L = M, L
@@ -40,14 +42,14 @@ class LowerTriangular:
         self._dev_idx = {}
 
     def forward(self, x):
-        out = torch.zeros(self.M, self.M, self.L, dtype=x.dtype, device=x.device)
         key = str(x.device)
         if key not in self._dev_idx:  # index tensors live on the device: no H2D copy per evaluation
             r, c = self._idx
-            self._dev_idx[key] = (torch.as_tensor(r, device=x.device), torch.as_tensor(c, device=x.device))
-        r, c = self._dev_idx[key]
-        out[r, c, :] = x.view(-1, self.L)
-        return out
+            self._dev_idx[key] = torch.as_tensor(r * self.M + c, device=x.device)
+        flat = self._dev_idx[key]
+        out = torch.zeros(self.L, self.M * self.M, dtype=x.dtype, device=x.device)
+        out = out.index_copy(1, flat, x.view(-1, self.L).t())
+        return out.view(self.L, self.M, self.M).permute(1, 2, 0)
 
     def backward(self, y):
         y = np.asarray(y)

@@ -41,13 +41,13 @@ class SVColourConvGP(SVGP):
         Z = self.Z()
         Kmm = self.kern.Kzz(Z) + torch.eye(M, dtype=Z.dtype, device=Z.device) * settings.jitter_level
         wc = self.wc()
-        mu, var = 0, 0
-        for c in range(C):
-            Xch = Xc[:, :, c].contiguous()
-            fmu, fvar = conditional(Xch, Z, self.kern.Kdiag(Xch), self.kern.Kzx(Z, Xch), Kmm, q_mu[:, :, c],
-                                    q_sqrt=q_sqrt[:, :, :, c], full_cov=full_cov, whiten=self.whiten)
-            mu, var = mu + fmu * wc[c], var + fvar * wc[c]
-        return mu, var
+        assert not full_cov
+        # the C channel conditionals share ONE factorisation of Kmm (the reference factorises it per channel)
+        from .conditional import conditional_shared
+        Xch = [Xc[:, :, c].contiguous() for c in range(C)]
+        Kdiag = torch.stack([self.kern.Kdiag(x) for x in Xch], dim=1)
+        Kmn = torch.stack([self.kern.Kzx(Z, x) for x in Xch], dim=2)
+        return conditional_shared(Kdiag, Kmn, Kmm, q_mu, q_sqrt, self.whiten, weights=wc)
 
 
 class SVConvGP(SVGP):

@@ -2,8 +2,9 @@
 (``GPflow.svgp.SVGP`` of the GPflow-inter-domain fork, mirrored in-tree by svconvgp.py:91-104 for
 the ELBO and misvgp.py:83-165 for the conditional).  Same constructor, parameters (Z, q_mu, q_sqrt)
 and methods (build_prior_KL, build_predict, build_likelihood, predict_y, compute_log_likelihood,
-_objective, get_free_state / set_state).  Kernel matrices come from the CUDA hot path; Cholesky /
-triangular solves / the batched L^T A product are library calls (cuSOLVER / cuBLAS through torch)."""
+_objective, get_free_state / set_state).  Kernel matrices come from the CUDA hot path; Cholesky, the
+triangular inverse, every GEMM of the conditional and of its reverse mode, and the variational projection are
+this library's own kernels (linalg.py -> csrc/linalg.cu); torch carries tensors and the autograd tape."""
 import numpy as np
 import torch
 
@@ -28,19 +29,24 @@ def gauss_kl_white_diag(q_mu, q_sqrt):
 
 
 def gauss_kl(q_mu, q_sqrt, K):
-    """KL[N(q_mu, S) || N(0, K)] summed over latents (GPflow 0.x gauss_kl / gauss_kl_diag)."""
+    """KL[N(q_mu, S) || N(0, K)] summed over latents (GPflow 0.x gauss_kl / gauss_kl_diag).  chol(K), the solves
+    against it and log|K| come from one ``linalg.chol_solve`` node (hand-written Cholesky / inverse / GEMM)."""
+    from . import linalg
     M, L_ = q_mu.shape
-    Lk = torch.linalg.cholesky(K)
-    alpha = torch.linalg.solve_triangular(Lk, q_mu, upper=False)
-    KL = 0.5 * (alpha ** 2).sum() + L_ * torch.log(torch.diagonal(Lk)).sum() - 0.5 * M * L_
+    if q_sqrt.dim() == 2:
+        rhs = torch.cat([q_mu, torch.eye(M, dtype=K.dtype, device=K.device)], 1)
+    else:
+        Lq = torch.tril(q_sqrt.permute(2, 0, 1))                              # (L, M, M)
+        rhs = torch.cat([q_mu, Lq.permute(1, 0, 2).reshape(M, L_ * M)], 1)    # [q_mu | Lq_1 | ... | Lq_L]
+    sol, _, logdet = linalg.chol_solve(K, rhs)                                # Lk^-1 rhs, sum log diag(Lk)
+    alpha, rest = sol[:, :L_], sol[:, L_:]
+    KL = 0.5 * (alpha ** 2).sum() + L_ * logdet - 0.5 * M * L_
     if q_sqrt.dim() == 2:
         KL = KL - 0.5 * torch.log(q_sqrt ** 2).sum()
-        Kinv = torch.cholesky_inverse(Lk)
-        return KL + 0.5 * (torch.diagonal(Kinv)[:, None] * q_sqrt ** 2).sum()
-    Lq = torch.tril(q_sqrt.permute(2, 0, 1))
+        kinv_diag = (rest ** 2).sum(0)                                        # diag(K^-1) = colsum(Lk^-1 ** 2)
+        return KL + 0.5 * (kinv_diag[:, None] * q_sqrt ** 2).sum()
     KL = KL - 0.5 * torch.log(torch.diagonal(Lq, dim1=1, dim2=2) ** 2).sum()
-    LiLq = torch.linalg.solve_triangular(Lk[None].expand(L_, -1, -1), Lq, upper=False)
-    return KL + 0.5 * (LiLq ** 2).sum()
+    return KL + 0.5 * (rest ** 2).sum()
 
 
 class Model(Parameterized):
@@ -245,7 +251,7 @@ class SVGP(Model):
         """Large-N forward sweep (the reference predicts 10 000 test images in batches of 1000 / 500 / 200,
         opt_tools/gpflow_tasks.py:70-90, cifar.py:44, and re-evaluates Kzz and its Cholesky for every
         batch): here ``Kuu``, its Cholesky, ``Li = Lm^-1`` and ``Lq^T Li`` are computed ONCE and every
-        batch costs one Kuf + Kdiag evaluation and two GEMMs.  Returns ``(mean, var)`` of y, or the log
+        batch costs one Kuf + Kdiag evaluation, one triangular GEMM and the fused projection.  Returns ``(mean, var)`` of y, or the log
         predictive density when ``density_Y`` is given.  Rows of ``Xnew`` are sharded over ranks when a
         process group is initialised (each rank returns its shard)."""
         if type(self).build_predict is not SVGP.build_predict:
@@ -254,26 +260,20 @@ class SVGP(Model):
                                       % type(self).__name__)
         if not (self.whiten and not self.q_diag):
             raise NotImplementedError("predict_batched covers the whitened full-covariance model")
+        from . import linalg
         with torch.no_grad():
             Xnew = parallel.shard_rows(as_tensor(Xnew))
             Yd = None if density_Y is None else parallel.shard_rows(as_tensor(density_Y))
             Z = self.Z()
             M = Z.shape[0]
             Kmm = self.kern.Kzz(Z) + torch.eye(M, dtype=Z.dtype, device=Z.device) * settings.jitter_level
-            Lm = torch.linalg.cholesky(Kmm)
-            Li = torch.linalg.solve_triangular(Lm, torch.eye(M, dtype=Z.dtype, device=Z.device), upper=False)
-            q_mu = self.q_mu()
-            Lq = torch.tril(self.q_sqrt().permute(2, 0, 1))          # (L, M, M)
-            LqtLi = Lq.transpose(1, 2) @ Li[None]                    # (L, M, M):  LTA = (Lq^T Li) Kmn
-            proj = Li.T @ q_mu                                       # fmean = Kmn^T Li^T q_mu
+            _, Li, _ = linalg.potrf_inv(Kmm)                       # once per sweep
+            q_mu, q_sqrt = self.q_mu(), self.q_sqrt()
             outs = []
             for s in range(0, Xnew.shape[0], batch_size):
                 xb = Xnew[s:s + batch_size]
-                Kmn = self.kern.Kzx(Z, xb)
-                A = Li @ Kmn
-                fmean = Kmn.T @ proj
-                LTA = LqtLi @ Kmn[None]
-                fvar = ((self.kern.Kdiag(xb) - (A * A).sum(0))[None, :] + (LTA * LTA).sum(1)).T
+                A = linalg.gemm(Li, self.kern.Kzx(Z, xb), a_tri=True)
+                fmean, fvar = linalg.project(A, q_mu, q_sqrt, self.kern.Kdiag(xb))  # LTA never leaves the kernel
                 if self.mean_function is not None:
                     fmean = fmean + self.mean_function(xb)
                 if Yd is None:

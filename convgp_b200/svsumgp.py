@@ -53,17 +53,14 @@ class FullSVSumGP(MeanFieldSVSumGP):
         self.q_sqrt = Param(_eye_stack(Mt, self.num_latent), LowerTriangular(Mt, self.num_latent))
 
     def build_predict(self, Xnew, full_cov=False):  # svsumgp.py:74-98
+        from . import linalg
         Z1, Z2 = self.Z1(), self.Z2()
         eye = lambda Z: torch.eye(Z.shape[0], dtype=Z.dtype, device=Z.device) * settings.jitter_level  # noqa: E731
-        Lm1 = torch.linalg.cholesky(self.kern1.Kzz(Z1) + eye(Z1))
-        Lm2 = torch.linalg.cholesky(self.kern2.Kzz(Z2) + eye(Z2))
-        A1 = torch.linalg.solve_triangular(Lm1, self.kern1.Kzx(Z1, Xnew), upper=False)
-        A2 = torch.linalg.solve_triangular(Lm2, self.kern2.Kzx(Z2, Xnew), upper=False)
-        A = torch.cat([A1, A2], 0)
-        diags = self.kern1.Kdiag(Xnew) + self.kern2.Kdiag(Xnew)
-        fvar = diags - (A1 ** 2).sum(0) - (A2 ** 2).sum(0)
-        fmean = A.T @ self.q_mu()
-        Lq = torch.tril(self.q_sqrt().permute(2, 0, 1))
-        LTA = Lq.transpose(1, 2) @ A[None]
-        fvar = (fvar[None, :] + (LTA ** 2).sum(1)).T
-        return fmean, fvar
+        # :77-84  Lm_i = chol(Kzz_i + jitter I), A_i = Lm_i^-1 Kzx_i  (hand-written Cholesky / inverse / GEMM)
+        A1, _, _ = linalg.chol_solve(self.kern1.Kzz(Z1) + eye(Z1), self.kern1.Kzx(Z1, Xnew))
+        A2, _, _ = linalg.chol_solve(self.kern2.Kzz(Z2) + eye(Z2), self.kern2.Kzx(Z2, Xnew))
+        A = torch.cat([A1, A2], 0)                                            # :86
+        diags = self.kern1.Kdiag(Xnew) + self.kern2.Kdiag(Xnew)               # :88
+        # :89-96  fvar = diags - sum A1^2 - sum A2^2 + sum (Lq^T A)^2, fmean = A^T q_mu: the fused projection on the
+        # stacked A with the (2M, 2M, L) variational factor
+        return linalg.project(A, self.q_mu(), self.q_sqrt(), diags)

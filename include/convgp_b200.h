@@ -145,6 +145,64 @@ const char* cgp_kernel_family(const cgp_kernel_desc* d, int32_t N, int32_t M, in
 int cgp_set_option(const char* name, int32_t value);
 int cgp_get_option(const char* name, int32_t* value);
 
+/* ---- the SVGP consumer's linear algebra (misvgp.py:128-163 conditional, svsumgp.py:75-96) ---------------------
+ * Row-major, caller-owned device buffers.  The reference's chain is tf.cholesky -> tf.matrix_triangular_solve ->
+ * batched tf.matmul (and TF autodiff through all of it); here: one factor-and-invert call, after which every solve of
+ * the forward and reverse pass is a GEMM with triangular structure, and a fused projection. */
+
+/* C = alpha * op(A) op(B)  (or C += with accumulate), op(X) = X^T when trans_x.  C is m x n, contraction length k.
+ * a_tri / b_tri: the STORED operand is lower-triangular -- entries above its diagonal are taken as zero and never
+ * read, and only the non-zero part of the K range is swept.  c_mode: 0 full; 1 only the lower triangle is computed,
+ * the strict upper part is written as zero (not touched when accumulating); 2 the lower triangle is computed and
+ * mirrored (for products known to be symmetric).  batch independent problems at the given element strides;
+ * batch_reduce: the batch products are summed into ONE C (requires accumulate; C pre-initialised by the caller). */
+typedef struct cgp_gemm_desc {
+  int32_t dtype;
+  int32_t m, n, k;
+  int32_t trans_a, trans_b;
+  int32_t a_tri, b_tri;
+  int32_t c_mode;
+  int32_t accumulate;
+  int32_t batch, batch_reduce;
+  int64_t lda, ldb, ldc;
+  int64_t stride_a, stride_b, stride_c;
+  double alpha;
+} cgp_gemm_desc;
+int cgp_gemm(const cgp_gemm_desc* d, const void* A, const void* B, void* C, void* stream);
+
+/* tf.cholesky (misvgp.py:128, svsumgp.py:77,81) + the inverse of the factor: A (n x n, lower part read) is
+ * overwritten by its Cholesky factor Lm (strict upper part zeroed), Li receives Lm^-1 (lower-triangular, upper part
+ * zeroed).  *info (DEVICE int) is set to 0, or to the order of the first leading minor that is not positive definite
+ * (TF raises there): cgp_potrf_check copies it back (synchronising `stream`) and returns CGP_ERR_NOT_PD with the
+ * index in cgp_last_error.  ws: cgp_potrf_inv_workspace bytes of scratch. */
+size_t cgp_potrf_inv_workspace(int32_t dtype, int32_t n);
+int cgp_potrf_inv(int32_t dtype, int32_t n, void* A, int64_t lda, void* Li, int64_t ldi, void* ws, size_t ws_bytes,
+                  int32_t* info, void* stream);
+int cgp_potrf_check(const int32_t* info, void* stream);
+
+/* The variational projection of the conditional (misvgp.py:138-163, svsumgp.py:88-96) from A = Lm^-1 Kmn (Mt x N;
+ * for the sum model the row-stacked [A1; A2]):
+ *     fmean (N, L) = A^T q_mu                                   q_mu (Mt, L)
+ *     fvar  (N, L) = Kdiag[n] - sum_m A^2 + sum_m (LTA_l)^2     q_kind 0: no q_sqrt term
+ *                                                               q_kind 1: q_sqrt (Mt, L) diagonal, LTA_l = A * q_sqrt[:, l]
+ *                                                               q_kind 2: q_sqrt (L, Mt, Mt) lower-triangular stack,
+ *                                                                         LTA_l = q_sqrt_l^T A (entries above the
+ *                                                                         diagonal ignored = tf.matrix_band_part)
+ * A_var (NULL = A): the matrix of the "- sum_m A^2" term when it differs from the projected one (not whitened:
+ * misvgp.py:138 uses Lm^-1 Kmn there and Lm^-T Lm^-1 Kmn everywhere else, :143-155).  q_stride: elements between
+ * consecutive q_sqrt_l matrices (0 = Mt * Mt).  Kdiag may be NULL (0).  accumulate != 0 adds into fmean / fvar instead of initialising them (multi-output models
+ * sum several projections).  LTA (L, Mt, N) is written when non-NULL (q_kind 2; the backward pass needs it) and
+ * otherwise never leaves the kernel. */
+int cgp_project_fwd(int32_t dtype, int32_t Mt, int32_t N, int32_t L, int32_t q_kind, int32_t accumulate, const void* A,
+                    const void* A_var, const void* q_mu, const void* q_sqrt, int64_t q_stride, const void* Kdiag,
+                    void* fmean, void* fvar, void* LTA, void* stream);
+/* Reverse mode of the above (TF autodiff upstream): dA (Mt, N), dq_mu (Mt, L), dq_sqrt (shape of q_sqrt; for q_kind 2
+ * the strict upper triangles are zero; always a contiguous (L, Mt, Mt) stack), dA_var (with A_var), dKdiag (N) or NULL
+ * are OVERWRITTEN.  LTA (q_kind 2) is consumed in place. */
+int cgp_project_bwd(int32_t dtype, int32_t Mt, int32_t N, int32_t L, int32_t q_kind, const void* A, const void* A_var,
+                    const void* q_mu, const void* q_sqrt, int64_t q_stride, void* LTA, const void* dfmean,
+                    const void* dfvar, void* dA, void* dA_var, void* dq_mu, void* dq_sqrt, void* dKdiag, void* stream);
+
 /* ---- data-parallel gradient exchange: one-shot peer-memory all-reduce -------------------------
  * One process per GPU.  cgp_comm_create allocates this rank's segment (the buffer the backward kernels accumulate
  * into, cgp_comm_local, and a local result buffer, cgp_comm_result); cgp_comm_handle exports its 64-byte CUDA IPC
