@@ -108,7 +108,7 @@ def lib():
     L.cgp_potrf_inv.argtypes = [i32, i32, vp, i64, vp, i64, vp, sz, vp, vp]
     L.cgp_potrf_check.argtypes = [vp, vp]
     L.cgp_project_fwd.argtypes = [i32] * 6 + [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
-    L.cgp_project_bwd.argtypes = [i32] * 5 + [vp, vp, vp, vp, i64] + [vp] * 9 + [vp]
+    L.cgp_project_bwd.argtypes = [i32] * 5 + [vp, vp, vp, vp, i64] + [vp] * 8 + [vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

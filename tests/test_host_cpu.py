@@ -29,6 +29,25 @@ def test_library_exports_every_declared_symbol():
     assert L.cgp_version() == 200
 
 
+def test_ctypes_argtypes_match_header_arity():
+    """Every prototype in include/convgp_b200.h has as many parameters as the ctypes binding declares (a mismatch
+    only shows up as a TypeError at the first call -- on the GPU box)."""
+    from convgp_b200 import _lib
+    L = _lib.lib()
+    src = open(os.path.join(ROOT, "include", "convgp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(cgp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
+    assert len(protos) >= 14
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        at = getattr(L, name).argtypes
+        if n == 0 and at is None:
+            continue
+        assert at is not None, name + ": no argtypes declared"
+        assert len(at) == n, (name, len(at), n)
+
+
 def test_descriptor_validation_without_gpu():
     from convgp_b200 import _lib
     s = _lib.Spec(torch.float64, 28, 28, 1, 5, 5, _lib.LAYOUT_PLANAR, _lib.OUT_SUM, 1, False, False)
