@@ -433,9 +433,57 @@ def step_bound(cfg, dtype_name, peaks, n_images, executed_only=False, kd_saved=T
     return sum(t_bound(*work[k]) for k in names)  # each kernel has its own binding pipe
 
 
+class Pipeline:
+    """Double-buffered end-to-end loop: while step i computes, a copy stream moves the minibatch of step i+1 from
+    pinned host memory into the other device buffer and the result of step i-1 back to pinned host memory.  Every
+    step still gets its own H2D copy of X and its own D2H read of the result; the host waits for the result of step
+    i-1 before it enqueues step i+1 (it is never more than one step ahead)."""
+
+    def __init__(self, h2d, compute, d2h):
+        import torch
+        self.h2d, self.compute, self.d2h = h2d, compute, d2h
+        self.copy = torch.cuda.Stream()
+
+    def run(self, n):
+        import torch
+        comp, copy = torch.cuda.current_stream(), self.copy
+        ev_h2d, ev_comp, ev_d2h = [None, None], [None, None], [None, None]
+        copy.wait_stream(comp)
+        with torch.cuda.stream(copy):
+            self.h2d(0)
+            ev_h2d[0] = torch.cuda.Event()
+            ev_h2d[0].record(copy)
+        for i in range(n):
+            b, nb = i % 2, (i + 1) % 2
+            if i + 1 < n:  # prefetch the next minibatch into the buffer step i-1 has finished with
+                with torch.cuda.stream(copy):
+                    if ev_comp[nb] is not None:
+                        copy.wait_event(ev_comp[nb])
+                    self.h2d(nb)
+                    ev_h2d[nb] = torch.cuda.Event()
+                    ev_h2d[nb].record(copy)
+            comp.wait_event(ev_h2d[b])
+            if ev_d2h[b] is not None:
+                comp.wait_event(ev_d2h[b])  # the result buffer of step i-2 has been read back
+            self.compute(b)
+            ev_comp[b] = torch.cuda.Event()
+            ev_comp[b].record(comp)
+            with torch.cuda.stream(copy):
+                copy.wait_event(ev_comp[b])
+                self.d2h(b)
+                ev_d2h[b] = torch.cuda.Event()
+                ev_d2h[b].record(copy)
+            if i >= 1:
+                ev_d2h[nb].synchronize()  # the host consumes the result of step i-1
+        if n:
+            ev_d2h[(n - 1) % 2].synchronize()
+        comp.wait_stream(copy)
+
+
 def measure_e2e(ctx, cfg, dtype_name, hp, inp, tens, steps):
     """The same step through the public kernel classes + torch autograd (host minibatch in, packed gradients + loss
-    out, every step; CUDA-graph replay when capturable) and straight over the C ABI (HotPath)."""
+    out, every step; CUDA-graph replay when capturable) and straight over the C ABI (HotPath).  Headline numbers are
+    double-buffered (Pipeline); the strictly serial copy -> compute -> copy -> wait loop is reported next to them."""
     import torch
     import torch.distributed as dist
     from convgp_b200 import convkernels as ck, kernels as bk
@@ -451,23 +499,23 @@ def measure_e2e(ctx, cfg, dtype_name, hp, inp, tens, steps):
     free = [conv.W.free, conv.basekern.variance.free, conv.basekern.lengthscales.free, kern.white.variance.free, Zp]
     X_host = torch.tensor(inp["X"], dtype=dt).pin_memory()
     n_out = sum(t.numel() for t in free) + 1
-    out_host = torch.empty(n_out, dtype=dt).pin_memory()
-    X_dev = torch.empty_like(tens["X"])
+    out_host = [torch.empty(n_out, dtype=dt).pin_memory() for _ in range(2)]
+    X_dev = [torch.empty_like(tens["X"]) for _ in range(2)]
 
-    def e2e_body():
-        X_dev.copy_(X_host, non_blocking=True)  # H2D of the minibatch (the reference feeds it per step)
+    def e2e_body(b):
         for t in free:
             t.grad = None
-        kuf, kd, kuu = kern.Kzx(Zp, X_dev), kern.Kdiag(X_dev), kern.Kzz(Zp)
+        kuf, kd, kuu = kern.Kzx(Zp, X_dev[b]), kern.Kdiag(X_dev[b]), kern.Kzz(Zp)
         loss = (kuf * tens["G"]).sum() + (kd * tens["gd"]).sum() + (kuu * tens["Gu"]).sum()
         loss.backward()
         return torch.cat([t.grad.reshape(-1) for t in free] + [loss.detach().reshape(1)])
 
     def e2e_eager_step():
-        packed = e2e_body()
+        X_dev[0].copy_(X_host, non_blocking=True)  # H2D of the minibatch (the reference feeds it per step)
+        packed = e2e_body(0)
         if world > 1:
             dist.all_reduce(packed)
-        out_host.copy_(packed, non_blocking=True)  # D2H of gradients + loss
+        out_host[0].copy_(packed, non_blocking=True)  # D2H of gradients + loss
         torch.cuda.current_stream().synchronize()
 
     def timed(fn, n):
@@ -479,71 +527,112 @@ def measure_e2e(ctx, cfg, dtype_name, hp, inp, tens, steps):
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
+    def timed_pipeline(pipe, n):
+        pipe.run(3)
+        ctx.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pipe.run(n)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
     for _ in range(3):
         e2e_eager_step()
     e2e_steps = max(10, min(steps, 100))
     e2e_eager_s = timed(e2e_eager_step, e2e_steps)
     ctx.launches += 6 * (e2e_steps + 3)
 
-    e2e_s, e2e_mode = e2e_eager_s, "eager"
+    e2e_s, e2e_serial_s, e2e_mode = e2e_eager_s, e2e_eager_s, "eager"
     if not ctx.args.no_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(3):
-                    e2e_body()
+                    e2e_body(0)
+                    e2e_body(1)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            g_e2e = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_e2e):
-                packed_static = e2e_body()
-                if world == 1:
-                    out_host.copy_(packed_static, non_blocking=True)
+            graphs, packed_static = [], []
+            for b in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    packed_static.append(e2e_body(b))
+                graphs.append(g)
 
-            def e2e_graph_step():
-                g_e2e.replay()
+            def compute(b):
+                graphs[b].replay()
                 if world > 1:
-                    dist.all_reduce(packed_static)
-                    out_host.copy_(packed_static, non_blocking=True)
+                    dist.all_reduce(packed_static[b])
+
+            def e2e_graph_step():  # strictly serial: copy in, compute, copy out, wait
+                X_dev[0].copy_(X_host, non_blocking=True)
+                compute(0)
+                out_host[0].copy_(packed_static[0], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
 
             e2e_graph_step()
-            ref_out = out_host.clone()
+            ref_out = out_host[0].clone()
             e2e_eager_step()
-            if not torch.allclose(ref_out, out_host, rtol=1e-6 if dtype_name == "f64" else 1e-3, atol=1e-6):
+            tol = dict(rtol=1e-6 if dtype_name == "f64" else 1e-3, atol=1e-6)
+            if not torch.allclose(ref_out, out_host[0], **tol):
                 raise RuntimeError("graph-replayed step disagrees with the eager step")
-            e2e_s, e2e_mode = timed(e2e_graph_step, e2e_steps), "cuda_graph"
-            ctx.launches += 6 * e2e_steps
+            e2e_serial_s = timed(e2e_graph_step, e2e_steps)
+            pipe = Pipeline(lambda b: X_dev[b].copy_(X_host, non_blocking=True), compute,
+                            lambda b: out_host[b].copy_(packed_static[b], non_blocking=True))
+            e2e_s = timed_pipeline(pipe, e2e_steps)
+            for b in range(2):  # both buffers of the pipelined loop hold the same step's result as the serial loop
+                if not torch.allclose(ref_out, out_host[b], **tol):
+                    raise RuntimeError("pipelined step disagrees with the serial step")
+            e2e_mode = "cuda_graph, double-buffered"
+            ctx.launches += 6 * (2 * e2e_steps + 3)
         except Exception as exc:  # keep the eager number, say why
-            e2e_mode = "eager (graph capture failed: %s)" % str(exc)[:120]
+            e2e_s, e2e_mode = e2e_serial_s, "eager (graph capture failed: %s)" % str(exc)[:120]
 
-    out_c = torch.empty(hp.grads.numel() + hp.Kdiag.numel(), dtype=dt).pin_memory()
+    # ---- straight over the C ABI: HotPath.step() on pre-allocated buffers
     ng = hp.grads.numel()
+    out_c = [torch.empty(ng + hp.Kdiag.numel(), dtype=dt).pin_memory() for _ in range(2)]
+    res_dev = [torch.empty(ng + hp.Kdiag.numel(), dtype=dt, device=dev) for _ in range(2)]
+    X_stage = [torch.empty_like(hp.X) for _ in range(2)]
+
+    def cabi_compute(b):
+        hp.X.copy_(X_stage[b], non_blocking=True)  # device-to-device: the step's graph reads the one static buffer
+        hp.step()
+        res_dev[b][:ng].copy_(hp.grads, non_blocking=True)
+        res_dev[b][ng:].copy_(hp.Kdiag.reshape(-1), non_blocking=True)
 
     def e2e_cabi_step():
-        hp.X.copy_(X_host, non_blocking=True)
-        hp.step()
-        out_c[:ng].copy_(hp.grads, non_blocking=True)
-        out_c[ng:].copy_(hp.Kdiag.reshape(-1), non_blocking=True)
+        X_stage[0].copy_(X_host, non_blocking=True)
+        cabi_compute(0)
+        out_c[0].copy_(res_dev[0], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     for _ in range(3):
         e2e_cabi_step()
-    e2e_cabi_s = timed(e2e_cabi_step, e2e_steps)
-    ctx.launches += hp.kernels_per_step * (e2e_steps + 3)
-    e2e_s, e2e_eager_s, e2e_cabi_s = ctx.max_over_ranks([e2e_s, e2e_eager_s, e2e_cabi_s])
+    e2e_cabi_serial_s = timed(e2e_cabi_step, e2e_steps)
+    pipe_c = Pipeline(lambda b: X_stage[b].copy_(X_host, non_blocking=True), cabi_compute,
+                      lambda b: out_c[b].copy_(res_dev[b], non_blocking=True))
+    e2e_cabi_s = timed_pipeline(pipe_c, e2e_steps)
+    ctx.launches += hp.kernels_per_step * (2 * e2e_steps + 6)
+    e2e_s, e2e_serial_s, e2e_eager_s, e2e_cabi_s, e2e_cabi_serial_s = ctx.max_over_ranks(
+        [e2e_s, e2e_serial_s, e2e_eager_s, e2e_cabi_s, e2e_cabi_serial_s])
     images = cfg.N * world
     h2d = cfg.N * cfg.H * cfg.W * cfg.C * es
     return {"value": images * e2e_steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": n_out * es, "steps": e2e_steps, "mode": e2e_mode,
+            "serial_value": images * e2e_steps / e2e_serial_s,
             "eager_value": images * e2e_steps / e2e_eager_s,
             "api": "kernel classes (Kzx / Kdiag / Kzz) + torch autograd; X from pinned host memory, packed "
-                   "gradients + loss back to host memory, every step",
+                   "gradients + loss back to host memory, every step.  value: double-buffered (the copy of step i+1's "
+                   "minibatch and the read-back of step i-1's result overlap step i's kernels; the host waits for "
+                   "every result, one step behind); serial_value: copy in -> compute -> copy out -> wait, one step at "
+                   "a time; eager_value: the same without CUDA-graph replay",
             "c_abi": {"value": images * e2e_steps / e2e_cabi_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
-                      "d2h_bytes_per_step": int(out_c.numel()) * es,
+                      "serial_value": images * e2e_steps / e2e_cabi_serial_s,
+                      "d2h_bytes_per_step": int(out_c[0].numel()) * es,
                       "api": "HotPath.step() over the C ABI (pre-allocated buffers, one CUDA graph incl. the gradient "
-                             "all-reduce), same host-to-device and device-to-host copies every step"}}
+                             "all-reduce), same host-to-device and device-to-host copies every step, double-buffered "
+                             "like value; serial_value: one step at a time"}}
 
 
 def _traffic(dtype_name, kernel):

@@ -22,7 +22,7 @@ EXPORTS = [
     "cgp_kernel_family", "cgp_set_option", "cgp_get_option",
     "cgp_comm_create", "cgp_comm_handle", "cgp_comm_connect", "cgp_comm_local", "cgp_comm_result",
     "cgp_comm_allreduce", "cgp_comm_status", "cgp_comm_destroy",
-    "cgp_gemm", "cgp_potrf_inv_workspace", "cgp_potrf_inv", "cgp_potrf_check", "cgp_project_fwd", "cgp_project_bwd",
+    "cgp_gemm", "cgp_potrf_inv_workspace", "cgp_potrf_inv", "cgp_potrf_check", "cgp_project_fwd", "cgp_project_bwd", "cgp_prob_is_largest", "cgp_bernoulli_ve",
 ]
 
 
@@ -109,6 +109,9 @@ def lib():
     L.cgp_potrf_check.argtypes = [vp, vp]
     L.cgp_project_fwd.argtypes = [i32] * 6 + [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     L.cgp_project_bwd.argtypes = [i32] * 5 + [vp, vp, vp, vp, i64] + [vp] * 8 + [vp]
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.cgp_prob_is_largest.argtypes = [i32, i32, i32, vp, vp, vp, i32, dp, dp, vp, vp, vp, vp]
+    L.cgp_bernoulli_ve.argtypes = [i32, i64, vp, vp, vp, i32, dp, dp, vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libconvgp_b200.so")
-SOURCES = ["api.cu", "probe.cu", "comm.cu", "linalg.cu"]
+SOURCES = ["api.cu", "probe.cu", "comm.cu", "linalg.cu", "likelihood.cu"]
 HEADERS = ["common.cuh", "fast.cuh", "kuu_fast.cuh", "mma64.cuh", "mma32.cuh", "umma32.cuh", "generic.cuh", "linalg.cuh", os.path.join("..", "..", "include", "convgp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--extended-lambda"] + os.environ.get("CGP_NVCC_EXTRA", "").split()
@@ -22,6 +22,7 @@ SOURCE_HEADERS = {  # which headers each translation unit includes (api.cu: ever
     "probe.cu": ["common.cuh", _ABI],
     "comm.cu": ["common.cuh", _ABI],
     "linalg.cu": ["common.cuh", "linalg.cuh", _ABI],
+    "likelihood.cu": ["common.cuh", _ABI],
 }
 
 

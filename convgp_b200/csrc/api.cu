@@ -165,14 +165,14 @@ static size_t fast_smem(const FastParams<T>& p, int tpb, bool bwd) {
 struct Options {
   int kuf_fwd = -1, kuf_bwd = -1, kdiag_fwd = -1, kdiag_bwd = -1;
   int kuf_fwd_f32 = -1, kuf_bwd_f32 = -1, kdiag_fwd_f32 = -1, kdiag_bwd_f32 = -1;
-  int kuf_dw_pass = -1, kuf_tiles = -1, tf32_tiles = -1, kdiag_warps = -1;
+  int kuf_dw_pass = -1, kuf_tiles = -1, tf32_tiles = -1, kdiag_warps = -1, kuf_bwd_split = -1, kuf_fwd_split = -1;
 };
 static Options g_opt;
 static int* option_slot(const char* name) {
   if (!name) return nullptr;
 #define OPT(n) if (!strcmp(name, #n)) return &g_opt.n;
   OPT(kuf_fwd) OPT(kuf_bwd) OPT(kdiag_fwd) OPT(kdiag_bwd) OPT(kuf_fwd_f32) OPT(kuf_bwd_f32) OPT(kdiag_fwd_f32)
-  OPT(kdiag_bwd_f32) OPT(kuf_dw_pass) OPT(kuf_tiles) OPT(tf32_tiles) OPT(kdiag_warps)
+  OPT(kdiag_bwd_f32) OPT(kuf_dw_pass) OPT(kuf_tiles) OPT(tf32_tiles) OPT(kdiag_warps) OPT(kuf_bwd_split) OPT(kuf_fwd_split)
 #undef OPT
   return nullptr;
 }
@@ -212,9 +212,11 @@ static std::mutex g_launch_mu;
 static std::map<LaunchKey, int> g_launch_occ;
 static std::map<std::pair<const void*, int>, size_t> g_launch_smem;
 
+// split2: the kernel understands FastParams::sub_split, and a unit of min_items_per_cta items may be cut in two
+// aligned halves when that is what it takes to fill the machine (2 * units <= resident CTA slots)
 template <typename K, typename P>
 static int launch_fast(K kernel, P& p, int tpb, size_t smem, cudaStream_t st, const char* name,
-                       long long min_items_per_cta = 1) {
+                       long long min_items_per_cta = 1, bool split2 = false) {
   if (smem > 227 * 1024) {
     set_error("%s: needs %zu bytes of shared memory", name, smem);
     return CGP_ERR_UNSUPPORTED;
@@ -246,6 +248,15 @@ static int launch_fast(K kernel, P& p, int tpb, size_t smem, cudaStream_t st, co
   }
   long long grid = std::min<long long>(p.n_items / min_items_per_cta, (long long)occ * num_sms());
   if (grid < 1) grid = 1;
+  p.sub_split = 0;
+  if (split2 && min_items_per_cta >= 2 && p.n_items % min_items_per_cta == 0) {
+    const long long units = p.n_items / min_items_per_cta;
+    if (2 * units <= (long long)occ * num_sms()) {
+      p.sub_split = 2;
+      p.unit_items = min_items_per_cta;
+      grid = 2 * units;
+    }
+  }
   p.tpb = tpb;
   kernel<<<(unsigned)grid, tpb, smem, st>>>(p);
   CGP_CUDA_CHECK(cudaGetLastError());
@@ -430,10 +441,15 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     const int nchunk_m = (M + rows_cta - 1) / rows_cta;
     p.n_items = (long long)nchunk_m * N * d->C * nblk;
     const size_t smem_m = mma_smem(p, BWD);
-    const long long unit_m = (long long)d->C * nblk;
+    // forward: every CTA walks at least one whole (chunk, image) unit, so an output element receives at most two
+    // atomic contributions and the result is order-independent.  The backward accumulates its gradients atomically
+    // from every CTA anyway, so its units may be split: with few images per rank (a row-sharded minibatch) the grid
+    // still fills the machine.  A CTA keeps at least 4 items (12 octets) between two flushes of its dZ registers.
+    const long long unit_m = (BWD && opt(g_opt.kuf_bwd_split, 1)) ? 4 : (long long)d->C * nblk;
+    const bool split_fwd = !BWD && opt(g_opt.kuf_fwd_split, 1) != 0;  // halves of a unit: exactly two contributions
 #define CALL(PH_, PW_)                                                                                   \
-  if (nt == 4) return launch_fast(kuf_mma_kernel<PH_, PW_, BWD, 4>, p, tpb_m, smem_m, st, "kuf", unit_m); \
-  return launch_fast(kuf_mma_kernel<PH_, PW_, BWD, 2>, p, tpb_m, smem_m, st, "kuf", unit_m)
+  if (nt == 4) return launch_fast(kuf_mma_kernel<PH_, PW_, BWD, 4>, p, tpb_m, smem_m, st, "kuf", unit_m, split_fwd); \
+  return launch_fast(kuf_mma_kernel<PH_, PW_, BWD, 2>, p, tpb_m, smem_m, st, "kuf", unit_m, split_fwd)
     CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL
   }

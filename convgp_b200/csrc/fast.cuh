@@ -40,6 +40,11 @@ struct FastParams {
   int ndom;  // Kdiag: pairing domains per image (1: all planes pair with each other, C: per plane)
   double Pn;  // the normaliser P (num_patches), as a double so that sum / P^k is one exact division
   long long n_items;
+  // Kuf forward, few images (row-sharded minibatch): each (row chunk, image) unit of unit_items items is cut into
+  // sub_split aligned pieces and every CTA owns exactly one piece, so an output element still receives exactly
+  // sub_split (= 2) atomic contributions -- order-independent -- while twice as many CTAs are in flight.  0: off.
+  int sub_split;
+  long long unit_items;
 };
 
 template <typename T>

@@ -105,8 +105,14 @@ __global__ void __launch_bounds__(128, BWD ? (NT == 4 ? 2 : 3) : (NT == 4 ? 3 : 
     for (int dt = 0; dt < DT; ++dt) off2[dt] = elem_off<PH, PW>(8 * dt + lr, p.Wd);
   }
 
-  const long long lo = p.n_items * blockIdx.x / gridDim.x;
-  const long long hi = p.n_items * (blockIdx.x + 1) / gridDim.x;
+  long long lo = p.n_items * blockIdx.x / gridDim.x;
+  long long hi = p.n_items * (blockIdx.x + 1) / gridDim.x;
+  if (p.sub_split > 1) {  // one aligned piece of a unit per CTA (FastParams::sub_split)
+    const long long piece = (p.unit_items + p.sub_split - 1) / p.sub_split;
+    const long long u = blockIdx.x / p.sub_split, k = blockIdx.x % p.sub_split;
+    lo = u * p.unit_items + min(k * piece, p.unit_items);
+    hi = u * p.unit_items + min((k + 1) * piece, p.unit_items);
+  }
   const int nblk = (p.Pc + 8 * kOctBlock - 1) / (8 * kOctBlock);
 
   T a[NT][KS];              // A fragments of the row tiles (scaled inducing patches)

@@ -140,7 +140,10 @@ const char* cgp_kernel_family(const cgp_kernel_desc* d, int32_t N, int32_t M, in
 
 /* Explicit kernel-family selection (all families are CUDA; there is no CPU path to select).  name: "kuf_fwd",
  * "kuf_bwd", "kdiag_fwd", "kdiag_bwd" (float64 families: 1 = dmma64, 0 = scalar) and the same with the suffix
- * "_f32" (2 = umma32, 1 = hmma32, 0 = scalar); "kuf_dw_pass" (1 = dW of Kuf from the stand-alone row-sum pass).
+ * "_f32" (2 = umma32, 1 = hmma32, 0 = scalar); "kuf_dw_pass" (1 = dW of Kuf from the stand-alone row-sum pass);
+ * "kuf_bwd_split" (float64 Kuf backward: 1 = a (row chunk, image) unit may be split over CTAs, the default; 0 = whole units);
+ * "kuf_fwd_split" (float64 Kuf forward with few images: 1 = units cut in two aligned halves when that fills the machine,
+ * the default -- still exactly two atomic contributions per output element; 0 = whole units).
  * value < 0 restores the default.  Process-wide; used by the variant tests and the profiling tools. */
 int cgp_set_option(const char* name, int32_t value);
 int cgp_get_option(const char* name, int32_t* value);
@@ -202,6 +205,22 @@ int cgp_project_fwd(int32_t dtype, int32_t Mt, int32_t N, int32_t L, int32_t q_k
 int cgp_project_bwd(int32_t dtype, int32_t Mt, int32_t N, int32_t L, int32_t q_kind, const void* A, const void* A_var,
                     const void* q_mu, const void* q_sqrt, int64_t q_stride, void* LTA, const void* dfmean,
                     const void* dfvar, void* dA, void* dA_var, void* dq_mu, void* dq_sqrt, void* dKdiag, void* stream);
+
+/* ---- variational expectations of the classification likelihoods (consumers of fmean / fvar: svconvgp.py:99-104) ----
+ * GPflow 0.x MultiClass (RobustMax) and Bernoulli (probit), by Gauss-Hermite quadrature; gh_x / gh_w: HOST arrays of
+ * the n_gh <= 64 nodes and weights (numpy.polynomial.hermite.hermgauss; the 1/sqrt(pi) is applied inside).
+ *
+ * cgp_prob_is_largest: p[n] = P(latent Y[n] is the largest) = sum_i w_i prod_{c != y} Phi((x_i - mu_c) / sqrt(var_c)),
+ * x_i = mu_y + sqrt(2 var_y) g_i, Phi mapped into [1e-4, 1 - 1e-4], variances floored at 1e-10.  Fmu, Fvar (N, L)
+ * row-major; Y (N) int32 device array.  dp_dmu / dp_dvar (N, L), both or neither: the derivatives, written by the same
+ * launch (TF autodiff upstream).  Y == NULL: p is (N, L), every class taken as the label in turn (predict_y). */
+int cgp_prob_is_largest(int32_t dtype, int32_t N, int32_t L, const void* Fmu, const void* Fvar, const int32_t* Y,
+                        int32_t n_gh, const double* gh_x, const double* gh_w, void* p, void* dp_dmu, void* dp_dvar,
+                        void* stream);
+/* ve[k] = sum_i w_i log(Y[k] == 1 ? q_i : 1 - q_i), q_i = Phi(mu + sqrt(2 var) g_i) (1 - 2e-3) + 1e-3, for n
+ * independent (Fmu, Fvar, Y) triples (Y in the kernels' dtype); dve_dmu / dve_dvar (n) may be NULL. */
+int cgp_bernoulli_ve(int32_t dtype, int64_t n, const void* Fmu, const void* Fvar, const void* Y, int32_t n_gh,
+                     const double* gh_x, const double* gh_w, void* ve, void* dve_dmu, void* dve_dvar, void* stream);
 
 /* ---- data-parallel gradient exchange: one-shot peer-memory all-reduce -------------------------
  * One process per GPU.  cgp_comm_create allocates this rank's segment (the buffer the backward kernels accumulate
