@@ -165,14 +165,14 @@ static size_t fast_smem(const FastParams<T>& p, int tpb, bool bwd) {
 struct Options {
   int kuf_fwd = -1, kuf_bwd = -1, kdiag_fwd = -1, kdiag_bwd = -1;
   int kuf_fwd_f32 = -1, kuf_bwd_f32 = -1, kdiag_fwd_f32 = -1, kdiag_bwd_f32 = -1;
-  int kuf_dw_pass = -1, kuf_tiles = -1, tf32_tiles = -1, kdiag_warps = -1, kuf_bwd_split = -1, kuf_fwd_split = -1;
+  int kuf_dw_pass = -1, kuf_tiles = -1, tf32_tiles = -1, kdiag_warps = -1, kuf_bwd_split = -1, kuf_fwd_split = -1, carveout = -1;
 };
 static Options g_opt;
 static int* option_slot(const char* name) {
   if (!name) return nullptr;
 #define OPT(n) if (!strcmp(name, #n)) return &g_opt.n;
   OPT(kuf_fwd) OPT(kuf_bwd) OPT(kdiag_fwd) OPT(kdiag_bwd) OPT(kuf_fwd_f32) OPT(kuf_bwd_f32) OPT(kdiag_fwd_f32)
-  OPT(kdiag_bwd_f32) OPT(kuf_dw_pass) OPT(kuf_tiles) OPT(tf32_tiles) OPT(kdiag_warps) OPT(kuf_bwd_split) OPT(kuf_fwd_split)
+  OPT(kdiag_bwd_f32) OPT(kuf_dw_pass) OPT(kuf_tiles) OPT(tf32_tiles) OPT(kdiag_warps) OPT(kuf_bwd_split) OPT(kuf_fwd_split) OPT(carveout)
 #undef OPT
   return nullptr;
 }
@@ -236,6 +236,8 @@ static int launch_fast(K kernel, P& p, int tpb, size_t smem, cudaStream_t st, co
         CGP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
       }
+      if (g_opt.carveout >= 0)  // same shared-memory carve-out for every kernel: kernels of parallel graph branches can share an SM
+        CGP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, g_opt.carveout));
       CGP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, tpb, smem));
       g_launch_occ[key] = occ;
     } else {
@@ -251,11 +253,9 @@ static int launch_fast(K kernel, P& p, int tpb, size_t smem, cudaStream_t st, co
   p.sub_split = 0;
   if (split2 && min_items_per_cta >= 2 && p.n_items % min_items_per_cta == 0) {
     const long long units = p.n_items / min_items_per_cta;
-    if (2 * units <= (long long)occ * num_sms()) {
-      p.sub_split = 2;
-      p.unit_items = min_items_per_cta;
-      grid = 2 * units;
-    }
+    p.sub_split = 2;
+    p.unit_items = min_items_per_cta;
+    grid = 2 * units;
   }
   p.tpb = tpb;
   kernel<<<(unsigned)grid, tpb, smem, st>>>(p);
@@ -396,6 +396,9 @@ static int run_umma_dz(const cgp_kernel_desc* d, const Geo& g, int N, int M, con
 #undef CALL
 }
 
+// float64 Kdiag: octets per work item (one octet per item was measured at 25-100 images per rank: no gain)
+static int kdiag_octs(long long, int) { return kOctBlock; }
+
 template <typename T, bool BWD>
 static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N, int M, const void* X,
                         const void* Z, const void* W, const void* var, const void* ls, const void* G, void* out,
@@ -437,6 +440,15 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     const int nt = opt(g_opt.kuf_tiles, 4);  // row tiles per warp (2 or 4)
     const int nblk = (g.Pc + 8 * kOctBlock - 1) / (8 * kOctBlock);
     const int tpb_m = 32 * pick_warps((M + (8 * nt) - 1) / (8 * nt) * 32, 1, 4);  // a warp covers 8*nt rows
+    // few images per rank (a row-sharded minibatch): fewer (row chunk, image) units than resident CTA slots -> the
+    // forward cuts every unit in two aligned halves, one per CTA (still exactly two contributions per output
+    // element).  Smaller CTAs were measured too (1-3 warps): the per-CTA image staging eats the gain.
+    bool split_fwd = false;
+    if (!BWD && opt(g_opt.kuf_fwd_split, 1) != 0) {
+      const int occ4 = nt == 4 ? 3 : 4;  // resident CTAs per SM (launch bounds of the forward kernel)
+      const long long units = (long long)((M + (tpb_m / 32) * 8 * nt - 1) / ((tpb_m / 32) * 8 * nt)) * N;
+      split_fwd = units < (long long)occ4 * num_sms();
+    }
     const int rows_cta = (tpb_m / 32) * 8 * nt;
     const int nchunk_m = (M + rows_cta - 1) / rows_cta;
     p.n_items = (long long)nchunk_m * N * d->C * nblk;
@@ -446,7 +458,6 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     // from every CTA anyway, so its units may be split: with few images per rank (a row-sharded minibatch) the grid
     // still fills the machine.  A CTA keeps at least 4 items (12 octets) between two flushes of its dZ registers.
     const long long unit_m = (BWD && opt(g_opt.kuf_bwd_split, 1)) ? 4 : (long long)d->C * nblk;
-    const bool split_fwd = !BWD && opt(g_opt.kuf_fwd_split, 1) != 0;  // halves of a unit: exactly two contributions
 #define CALL(PH_, PW_)                                                                                   \
   if (nt == 4) return launch_fast(kuf_mma_kernel<PH_, PW_, BWD, 4>, p, tpb_m, smem_m, st, "kuf", unit_m, split_fwd); \
   return launch_fast(kuf_mma_kernel<PH_, PW_, BWD, 2>, p, tpb_m, smem_m, st, "kuf", unit_m, split_fwd)
@@ -513,7 +524,8 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
   if constexpr (std::is_same<T, double>::value) if (mma_path) {
     const int Lsweep = std::min(Pd, Pd / 2 + 32);
     const int noct = (Lsweep + 7) / 8;
-    p.S = (noct + kOctBlock - 1) / kOctBlock;
+    p.octs = kdiag_octs((long long)N * p.ndom * nchunk, noct);
+    p.S = (noct + p.octs - 1) / p.octs;
     p.n_items = (long long)N * p.ndom * nchunk * p.S;
     const size_t smem_m = mma_smem(p, BWD);
 #define CALL(PH_, PW_) return launch_fast(kdiag_mma_kernel<PH_, PW_, BWD>, p, tpb, smem_m, st, "kdiag")
@@ -574,7 +586,8 @@ static int run_kdiag_saved_fwd(const cgp_kernel_desc* d, const Geo& g, int mode,
     const int nchunk = (Pd + tpb - 1) / tpb;
     const int Lsweep = std::min(Pd, Pd / 2 + 32);
     const int noct = (Lsweep + 7) / 8;
-    p.S = (noct + kOctBlock - 1) / kOctBlock;
+    p.octs = kdiag_octs((long long)N * nchunk, noct);
+    p.S = (noct + p.octs - 1) / p.octs;
     p.n_items = (long long)N * nchunk * p.S;
     const size_t smem_m = mma_smem(p, true);
 #define CALL(PH_, PW_) return launch_fast(kdiag_mma_kernel<PH_, PW_, true>, p, tpb, smem_m, st, "kdiag")
@@ -646,7 +659,11 @@ static int run_kuu_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int M,
   const int Dp = d->ph * d->pw;
   const size_t smem = sizeof(T) * ((size_t)JT * Dp + JT + Math<T>::kTableDoubles);
   dim3 grid(nic, njc);
-#define CALL(PH_, PW_) kuu_fast_kernel<T, PH_ * PW_, BWD><<<grid, kKuuTPB, smem, st>>>(p)
+#define CALL(PH_, PW_)                                                                                              \
+  if (g_opt.carveout >= 0)                                                                                          \
+    cudaFuncSetAttribute(kuu_fast_kernel<T, PH_ * PW_, BWD>, cudaFuncAttributePreferredSharedMemoryCarveout,         \
+                         g_opt.carveout);                                                                           \
+  kuu_fast_kernel<T, PH_ * PW_, BWD><<<grid, kKuuTPB, smem, st>>>(p)
   CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL
   CGP_CUDA_CHECK(cudaGetLastError());

@@ -45,6 +45,7 @@ struct FastParams {
   // sub_split (= 2) atomic contributions -- order-independent -- while twice as many CTAs are in flight.  0: off.
   int sub_split;
   long long unit_items;
+  int octs;  // float64 Kdiag: patch octets per work item (1..kOctBlock; finer items balance a small grid's load)
 };
 
 template <typename T>

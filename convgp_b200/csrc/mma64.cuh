@@ -690,9 +690,8 @@ __global__ void __launch_bounds__(kMaxTPB, 1) kdiag_mma_kernel(const FastParams<
       }
     };
     const bool warp_full = wbase + 31 < Pd;
-#pragma unroll
-    for (int ob = 0; ob < kOctBlock; ++ob) {
-      const int v0i = (blk * kOctBlock + ob) * 8;  // visit index of the octet's first column
+    for (int ob = 0; ob < p.octs; ++ob) {
+      const int v0i = (blk * p.octs + ob) * 8;  // visit index of the octet's first column
       if (v0i >= Lsweep) continue;
       // delta = vi - k, k in [0, 31]: interior iff 0 < v0i - 31 and v0i + 7 < half (and inside the sweep)
       if (warp_full && v0i >= 32 && v0i + 7 < half && v0i + 7 < Lsweep) octet(v0i, std::true_type{});
