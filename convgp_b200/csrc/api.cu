@@ -475,10 +475,14 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     const int nchunk_m = (M + rows_cta - 1) / rows_cta;
     p.n_items = (long long)nchunk_m * N * d->C * nblk;
     const size_t smem_m = mma_smem(p, BWD);
-    const long long unit_m = (long long)d->C * nblk;
+    // same launch shapes as the float64 family: backward units split freely, forward units cut in two aligned halves
+    // when the whole units do not fill the CTA slots (config 5: 30 images x 4 row chunks = 120 units on 148 SMs)
+    const long long unit_m = (BWD && opt(g_opt.kuf_bwd_split, 1)) ? 4 : (long long)d->C * nblk;
+    const bool split32 = !BWD && opt(g_opt.kuf_fwd_split, 1) != 0 &&
+                         (long long)nchunk_m * N < 3LL * num_sms();
 #define CALL(PH_, PW_)                                                                                    \
-  if (nt == 4) return launch_fast(kuf_tf32_kernel<PH_, PW_, BWD, 4>, p, tpb_m, smem_m, st, "kuf", unit_m); \
-  return launch_fast(kuf_tf32_kernel<PH_, PW_, BWD, 2>, p, tpb_m, smem_m, st, "kuf", unit_m)
+  if (nt == 4) return launch_fast(kuf_tf32_kernel<PH_, PW_, BWD, 4>, p, tpb_m, smem_m, st, "kuf", unit_m, split32); \
+  return launch_fast(kuf_tf32_kernel<PH_, PW_, BWD, 2>, p, tpb_m, smem_m, st, "kuf", unit_m, split32)
     CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL
   }

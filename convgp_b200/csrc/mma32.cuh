@@ -94,8 +94,14 @@ __global__ void __launch_bounds__(128, BWD ? 2 : 3) kuf_tf32_kernel(const FastPa
 #pragma unroll
   for (int r = 0; r < R; ++r) offr[r] = elem_off<PH, PW>(8 * KS + r, p.Wd);
 
-  const long long lo = p.n_items * blockIdx.x / gridDim.x;
-  const long long hi = p.n_items * (blockIdx.x + 1) / gridDim.x;
+  long long lo = p.n_items * blockIdx.x / gridDim.x;
+  long long hi = p.n_items * (blockIdx.x + 1) / gridDim.x;
+  if (p.sub_split > 1) {  // one aligned piece of a unit per CTA (FastParams::sub_split)
+    const long long piece = (p.unit_items + p.sub_split - 1) / p.sub_split;
+    const long long u = blockIdx.x / p.sub_split, k = blockIdx.x % p.sub_split;
+    lo = u * p.unit_items + min(k * piece, p.unit_items);
+    hi = u * p.unit_items + min((k + 1) * piece, p.unit_items);
+  }
   const int nblk = (p.Pc + 8 * kOctBlock - 1) / (8 * kOctBlock);
   const int rows_per_cta = (int)(blockDim.x >> 5) * 16 * NT;
 

@@ -19,6 +19,57 @@ def as_tensor(x, dtype=None):
                            device=settings.device)
 
 
+_SIDE_STREAMS = {}
+
+
+def concurrent(*thunks):
+    """Evaluate independent thunks on parallel CUDA streams (fork / join with events) and return their results in
+    order.  Kzx, Kdiag and Kzz of one SVGP evaluation do not depend on each other, and each of the library's kernels
+    is a persistent grid: on parallel streams the ramp-up / tail of one overlaps the body of another.  Autograd replays
+    every backward node on the stream its forward ran on, so the three backward kernels overlap the same way.
+    Capturable in a CUDA graph (the side streams join the capture through the fork event).  CPU tensors / a single
+    thunk: plain sequential evaluation."""
+    if len(thunks) < 2 or not torch.cuda.is_available() or settings.device.type != "cuda":
+        return [t() for t in thunks]
+    main = torch.cuda.current_stream()
+    key = (main.device, len(thunks) - 1)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=main.device) for _ in range(len(thunks) - 1)]
+        # leaves shared by the branches (Z, W, variance, lengthscales) accumulate their gradient on the stream they were
+        # created on; the engine synchronises the branch streams with it -- intended here, not a mistake to warn about
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
+    side = _SIDE_STREAMS[key]
+    fork = torch.cuda.Event()
+    fork.record(main)
+    outs = [None] * len(thunks)
+    for st, i in zip(side, range(1, len(thunks))):
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            outs[i] = thunks[i]()
+    outs[0] = thunks[0]()
+    for st, o in zip(side, outs[1:]):
+        main.wait_stream(st)
+        for t in (o if isinstance(o, (tuple, list)) else (o,)):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(main)  # allocated on the side stream, consumed on the main one
+    return outs
+
+
+def svgp_terms(kern, Z, X, jitter=None):
+    """(Kdiag(X), Kzx(Z, X), Kzz(Z) + jitter I): the three kernel evaluations of one SVGP prediction
+    (misvgp.py:194-201, svsumgp.py:76-88; GPflow's SVGP.build_predict), on parallel streams (``concurrent``)."""
+    jitter = settings.jitter_level if jitter is None else jitter
+
+    def kzz():
+        K = kern.Kzz(Z)
+        return K + torch.eye(Z.shape[0], dtype=Z.dtype, device=Z.device) * jitter
+
+    kzx, kdiag, kmm = concurrent(lambda: kern.Kzx(Z, X), lambda: kern.Kdiag(X), kzz)
+    return kdiag, kzx, kmm
+
+
 class Kern(Parameterized):
     def __init__(self, input_dim, active_dims=None):
         self.input_dim = int(input_dim)

@@ -68,13 +68,12 @@ class MultiOutputInducingSVGP(_svgp_base()):
         self.q_sqrt = Param(q_sqrt, LowerTriangular(M, C * L))
 
     def build_predict(self, Xnew, full_cov=False):
-        from .settings import settings
+        from .kernels import svgp_terms
         M, L, C = self.num_inducing, self.num_latent, self.kern.inducing_outputs
         q_mu = self.q_mu().reshape(M, L, C)
         q_sqrt = self.q_sqrt().reshape(M, M, L, C)
         Z = self.Z()
-        Kdiag, Kmn = self.kern.Kdiag(Xnew), self.kern.Kzx(Z, Xnew)
-        Kmm = self.kern.Kzz(Z) + torch.eye(M, dtype=Z.dtype, device=Z.device) * settings.jitter_level
+        Kdiag, Kmn, Kmm = svgp_terms(self.kern, Z, Xnew)
         if full_cov:
             raise NotImplementedError("full_cov")
         from .conditional import conditional_shared  # the C channel conditionals share ONE factorisation of Kmm

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import parallel
-from .kernels import as_tensor
+from .kernels import as_tensor, svgp_terms
 from .misvgp import conditional
 from .param import LowerTriangular, Param, Parameterized, Positive
 from .settings import settings
@@ -217,8 +217,8 @@ class SVGP(Model):
 
     def build_predict(self, Xnew, full_cov=False):
         Z = self.Z()
-        Kmm = self.kern.Kzz(Z) + torch.eye(Z.shape[0], dtype=Z.dtype, device=Z.device) * settings.jitter_level
-        mu, var = conditional(Xnew, Z, self.kern.Kdiag(Xnew), self.kern.Kzx(Z, Xnew), Kmm, self.q_mu(),
+        Kdiag, Kmn, Kmm = svgp_terms(self.kern, Z, Xnew)  # three independent kernel evaluations, parallel streams
+        mu, var = conditional(Xnew, Z, Kdiag, Kmn, Kmm, self.q_mu(),
                               full_cov=full_cov, q_sqrt=self.q_sqrt(), whiten=self.whiten)
         if self.mean_function is not None:
             mu = mu + self.mean_function(Xnew)

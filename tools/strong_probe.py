@@ -50,6 +50,8 @@ def timeline(dtype="f64", rows=25, cfgkey="cfg3"):
     ctx = bench.Ctx(_Args())
     cfg = bench.CONFIGS[cfgkey]
     hp, _, _, _ = bench.build_hotpath(ctx, cfg, dtype, 0, rows=(0, rows), gu_scale=1.0, collective=False)
+    if os.environ.get("CGP_BRANCH_ORDER"):
+        hp.branch_order = os.environ["CGP_BRANCH_ORDER"]
     hp.capture(overlapped=True)
     for _ in range(5):
         hp.step()
