@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libconvgp_b200.so")
 SOURCES = ["api.cu", "probe.cu", "comm.cu", "linalg.cu", "likelihood.cu"]
-HEADERS = ["common.cuh", "fast.cuh", "kuu_fast.cuh", "mma64.cuh", "mma32.cuh", "umma32.cuh", "generic.cuh", "linalg.cuh", os.path.join("..", "..", "include", "convgp_b200.h")]
+HEADERS = ["common.cuh", "fast.cuh", "kuu_fast.cuh", "mma64.cuh", "mma32.cuh", "umma32.cuh", "umma16.cuh", "generic.cuh", "linalg.cuh", os.path.join("..", "..", "include", "convgp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--extended-lambda"] + os.environ.get("CGP_NVCC_EXTRA", "").split()
 

@@ -14,6 +14,7 @@
 #include "mma64.cuh"
 #include "mma32.cuh"
 #include "umma32.cuh"
+#include "umma16.cuh"
 #include "generic.cuh"
 
 namespace cgp {
@@ -271,6 +272,7 @@ static int launch_fast(K kernel, P& p, int tpb, size_t smem, cudaStream_t st, co
 
 #ifdef CGP_UMMA_TRACE
 static long long* g_umma_trace = nullptr;
+static long long* g_umma16_trace = nullptr;
 #endif
 // ---- float32 tcgen05 (UMMA) family: single-channel images, one RBF over the whole patch -------------
 static bool umma_ok(const cgp_kernel_desc* d, const Geo& g, int mode, int M) {
@@ -346,6 +348,132 @@ static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int
 #undef CALL
 }
 
+// ---- float32 tcgen05 family, second generation (umma16.cuh): two fp16 terms per operand, both operands in shared
+// memory, nothing restaged per tile.  Planar layout with one RBF (fast mode 1), any channel count, summed output.
+static bool umma16_kuf_plan(const cgp_kernel_desc* d, const Geo& g, int mode, int M, int* nbuf_out) {
+  if (mode != 1 || d->dtype != CGP_F32 || d->out_mode == CGP_OUT_PER_CHANNEL) return false;
+  const int KP = umma16::pad_k(g.D), TN = 192;
+  const int n_pt = (g.P + TN - 1) / TN, n_zt = (M + umma16::TM - 1) / umma16::TM;
+  for (int nbuf = 3; nbuf >= 2; --nbuf)
+    if (umma16::kuf_smem_plan(KP, TN, d->H * d->W * d->C, n_pt * TN, n_zt * umma16::TM, nbuf).total <= 227 * 1024) {
+      if (nbuf_out) *nbuf_out = nbuf;
+      return true;
+    }
+  return false;
+}
+
+static int run_umma16_kuf_fwd(const cgp_kernel_desc* d, const Geo& g, int N, int M, const void* X, const void* Z,
+                              const void* W, const void* var, const void* ls, void* out, cudaStream_t st) {
+  constexpr int TN = 192;
+  umma16::Params p;
+  memset(&p, 0, sizeof(p));
+  int nbuf = 0;
+  if (!umma16_kuf_plan(d, g, 1, M, &nbuf)) { set_error("umma16 kuf: shared-memory plan does not fit"); return CGP_ERR_UNSUPPORTED; }
+  p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
+  p.ls = (const float*)ls; p.out = (float*)out;
+  p.N = N; p.M = M; p.H = d->H; p.Wd = d->W; p.C = d->C; p.Hout = g.Hout; p.Wout = g.Wout; p.Pc = g.Pc; p.P = g.P; p.D = g.D;
+  p.n_pt = (g.P + TN - 1) / TN;
+  p.n_zt = (M + umma16::TM - 1) / umma16::TM;
+  p.Mpad = p.n_zt * umma16::TM;
+  p.nbuf = nbuf;
+  p.n_units = (long long)N * p.n_pt * p.n_zt;
+  p.Pn = (float)g.P;
+  if (p.n_units < 1) return CGP_OK;
+#ifdef CGP_UMMA_TRACE
+  {
+    static long long* tr = nullptr;
+    if (!tr) { cudaMalloc(&tr, 256 * 16 * sizeof(long long)); }
+    cudaMemsetAsync(tr, 0, 256 * 16 * sizeof(long long), st);
+    p.trace = tr;
+    g_umma16_trace = tr;
+  }
+#endif
+  const size_t smem = umma16::kuf_smem_plan(umma16::pad_k(g.D), TN, d->H * d->W * d->C, p.n_pt * TN, p.Mpad, nbuf).total;
+  const long long grid = std::max<long long>(1, std::min<long long>(p.n_units, num_sms()));
+  int dev = 0;
+  CGP_CUDA_CHECK(cudaGetDevice(&dev));
+#define CALL(PH_, PW_)                                                                                        \
+  {                                                                                                           \
+    void (*kernel)(const umma16::Params) = umma16::kuf_fwd_kernel<PH_, PW_, TN>;                              \
+    {                                                                                                         \
+      std::lock_guard<std::mutex> lk(g_launch_mu);                                                            \
+      size_t& cur = g_launch_smem[std::make_pair((const void*)kernel, dev)];                                  \
+      if (smem > cur) {                                                                                       \
+        CGP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        cur = smem;                                                                                           \
+      }                                                                                                       \
+    }                                                                                                         \
+    kernel<<<(unsigned)grid, umma16::kThreads, smem, st>>>(p);                                                \
+    CGP_CUDA_CHECK(cudaGetLastError());                                                                       \
+    return CGP_OK;                                                                                            \
+  }
+  CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+}
+
+// Kdiag forward (umma16.cuh kdiag_fwd_kernel): one pairing domain per image, tiles on or above the diagonal only.
+static bool umma16_kdiag_plan(const cgp_kernel_desc* d, const Geo& g, int mode, int* nbuf_out) {
+  if (mode != 1 || d->dtype != CGP_F32 || d->out_mode == CGP_OUT_PER_CHANNEL) return false;
+  const int KD = umma16::pad_kd(g.D), nt = (g.P + 127) / 128;
+  for (int nbuf = 2; nbuf >= 1; --nbuf)
+    if (umma16::kd_smem_plan(KD, d->H * d->W * d->C, nt * 128, nbuf).total <= 227 * 1024) {
+      if (nbuf_out) *nbuf_out = nbuf;
+      return true;
+    }
+  return false;
+}
+
+static int run_umma16_kdiag(const cgp_kernel_desc* d, const Geo& g, int N, const void* X, const void* W,
+                            const void* var, const void* ls, void* out, void* save, cudaStream_t st) {
+  umma16::KdParams p;
+  memset(&p, 0, sizeof(p));
+  int nbuf = 0;
+  if (!umma16_kdiag_plan(d, g, 1, &nbuf)) { set_error("umma16 kdiag: shared-memory plan does not fit"); return CGP_ERR_UNSUPPORTED; }
+  p.X = (const float*)X; p.Wt = (const float*)W; p.var = (const float*)var; p.ls = (const float*)ls;
+  p.out = (float*)out; p.save = (float*)save;
+  p.N = N; p.H = d->H; p.Wd = d->W; p.C = d->C; p.Wout = g.Wout; p.Pc = g.Pc; p.P = g.P;
+  p.nt = (g.P + 127) / 128;
+  p.NL = (g.P - 128 * (p.nt - 1)) <= 64 ? 64 : 128;
+  p.Rpad = p.nt * 128;
+  p.nbuf = nbuf;
+  p.cost_img = 0;
+  for (int i = 0; i < p.nt; ++i)
+    for (int j = i; j < p.nt; ++j) p.cost_img += j == p.nt - 1 ? p.NL / 64 : 2;
+  p.Pn = (float)g.P;
+  if (N < 1) return CGP_OK;
+  const size_t smem = umma16::kd_smem_plan(umma16::pad_kd(g.D), d->H * d->W * d->C, p.Rpad, nbuf).total;
+  const long long units = (long long)N * p.nt * (p.nt + 1) / 2;
+  const long long grid = std::max<long long>(1, std::min<long long>(units, num_sms()));
+  int dev = 0;
+  CGP_CUDA_CHECK(cudaGetDevice(&dev));
+#define CALL(PH_, PW_)                                                                                        \
+  {                                                                                                           \
+    void (*kernel)(const umma16::KdParams) = umma16::kdiag_fwd_kernel<PH_, PW_>;                              \
+    {                                                                                                         \
+      std::lock_guard<std::mutex> lk(g_launch_mu);                                                            \
+      size_t& cur = g_launch_smem[std::make_pair((const void*)kernel, dev)];                                  \
+      if (smem > cur) {                                                                                       \
+        CGP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        cur = smem;                                                                                           \
+      }                                                                                                       \
+    }                                                                                                         \
+    kernel<<<(unsigned)grid, umma16::kThreads, smem, st>>>(p);                                                \
+    CGP_CUDA_CHECK(cudaGetLastError());                                                                       \
+    return CGP_OK;                                                                                            \
+  }
+  CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+}
+
+// float32 Kdiag forward family: 3 umma16 | 2 umma32 | 1 hmma32 | 0 scalar (what the option asks for, lowered to
+// what the configuration supports)
+static int kdiag_fwd_f32_family(const cgp_kernel_desc* d, const Geo& g, int mode) {
+  int fam = opt(g_opt.kdiag_fwd_f32, 3);
+  if (fam == 3 && !umma16_kdiag_plan(d, g, mode, nullptr)) fam = 2;
+  if (fam == 2 && !umma_ok(d, g, mode, 0)) fam = 1;
+  return fam;
+}
+
 // dZ / dvariance / dlengthscale of Kuf (umma32.cuh kuf_dz_kernel): one row tile of 128 inducing
 // patches per CTA group, the (image, patch tile) units of the tile split evenly over the group.
 static int run_umma_dz(const cgp_kernel_desc* d, const Geo& g, int N, int M, const void* X, const void* Z,
@@ -414,7 +542,10 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
   }
   if constexpr (std::is_same<T, float>::value) {
-    const int fam = opt(BWD ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 2);  // 2 umma32 | 1 hmma32 | 0 scalar
+    int fam = opt(BWD ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 3);  // 3 umma16 | 2 umma32 | 1 hmma32 | 0 scalar
+    if (!BWD && fam == 3 && umma16_kuf_plan(d, g, mode, M, nullptr))
+      return run_umma16_kuf_fwd(d, g, N, M, X, Z, W, var, ls, out, st);
+    if (fam == 3) fam = 2;
     if (fam == 2 && umma_ok(d, g, mode, M) &&
         umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total <= 227 * 1024) {
       if (!BWD) return run_umma_rowsum(0, d, g, N, M, X, Z, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st);
@@ -464,7 +595,7 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
 #undef CALL
   }
-  const int use_tc = opt(BWD ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 2);
+  const int use_tc = opt(BWD ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 3);
   if constexpr (std::is_same<T, float>::value) if (use_tc) {
     // float32: 3xTF32 tensor-core kernels
     const int nt_env = opt(g_opt.tf32_tiles, 0);
@@ -510,7 +641,7 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
   p.ndom = (mode == 2 || p.out_per_channel) ? d->C : 1;
   const int ppd = d->C / p.ndom, Pd = ppd * g.Pc, Hd = ppd * g.Hout;
   const int use_mma = opt(BWD ? g_opt.kdiag_bwd : g_opt.kdiag_fwd, 1);
-  const int use_tc32 = opt(BWD ? g_opt.kdiag_bwd_f32 : g_opt.kdiag_fwd_f32, 2);
+  const int use_tc32 = opt(BWD ? g_opt.kdiag_bwd_f32 : g_opt.kdiag_fwd_f32, 3);
   const bool mma_path = std::is_same<T, double>::value ? use_mma != 0 : use_tc32 != 0;
   // the MMA kernels hold ~200-250 registers per thread: small CTAs keep several resident per SM
   const int max_warps_env = opt(g_opt.kdiag_warps, 0);
@@ -522,7 +653,9 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
     CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
   }
   if constexpr (std::is_same<T, float>::value) {
-    if (use_tc32 == 2 && umma_ok(d, g, mode, 0))
+    if (!BWD && kdiag_fwd_f32_family(d, g, mode) == 3)
+      return run_umma16_kdiag(d, g, N, X, W, var, ls, out, nullptr, st);
+    if (use_tc32 >= 2 && umma_ok(d, g, mode, 0))
       return run_umma_rowsum(BWD ? 2 : 1, d, g, N, 0, X, nullptr, W, var, ls, G, out, dW, dvar, dls, st);
   }
   if constexpr (std::is_same<T, double>::value) if (mma_path) {
@@ -566,7 +699,7 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
 static bool kdiag_saved_ok(const cgp_kernel_desc* d, const Geo& g, int mode) {
   if (mode != 1 || d->out_mode == CGP_OUT_PER_CHANNEL) return false;
   if (d->dtype == CGP_F32)
-    return opt(g_opt.kdiag_fwd_f32, 2) == 2 && opt(g_opt.kdiag_bwd_f32, 2) == 2 && umma_ok(d, g, mode, 0);
+    return kdiag_fwd_f32_family(d, g, mode) >= 2 && opt(g_opt.kdiag_bwd_f32, 3) >= 2;
   return opt(g_opt.kdiag_fwd, 1) != 0 && opt(g_opt.kdiag_bwd, 1) != 0;
 }
 
@@ -576,6 +709,7 @@ static int run_kdiag_saved_fwd(const cgp_kernel_desc* d, const Geo& g, int mode,
   CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(T) * (size_t)N, st));
   CGP_CUDA_CHECK(cudaMemsetAsync(save, 0, sizeof(T) * (size_t)N * (g.P + 2), st));
   if constexpr (std::is_same<T, float>::value) {
+    if (kdiag_fwd_f32_family(d, g, mode) == 3) return run_umma16_kdiag(d, g, N, X, W, var, ls, out, save, st);
     return run_umma_rowsum(4, d, g, N, 0, X, nullptr, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st, save);
   } else {
     FastParams<T> p;
@@ -730,6 +864,28 @@ int cgp_umma_trace_dump(void) {
 }
 #endif
 
+#ifdef CGP_UMMA_TRACE
+// development only: %globaltimer stamps of every CTA of the last umma16 launch, ns after the first CTA's entry
+int cgp_umma16_trace_dump(void) {
+  if (!g_umma16_trace) return 0;
+  static long long h[256 * 16];
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, g_umma16_trace, sizeof(h), cudaMemcpyDeviceToHost);
+  long long t0 = 0;
+  for (int b = 0; b < 256; ++b) if (h[b * 16] && (!t0 || h[b * 16] < t0)) t0 = h[b * 16];
+  const char* names[12] = {"entry", "prologue done", "first image landed", "first tile staged", "issuer: Z ready",
+                           "issuer: first tile", "epi: Z staged", "epi: first acc", "epi: last unit", "epi: flushed",
+                           "exit", ""};
+  for (int s = 0; s < 11; ++s) {
+    long long mn = 1LL << 60, mx = 0, sum = 0; int cnt = 0;
+    for (int b = 0; b < 256; ++b) { const long long v = h[b * 16 + s]; if (!v) continue; const long long d = v - t0; mn = d < mn ? d : mn; mx = d > mx ? d : mx; sum += d; ++cnt; }
+    if (cnt) printf("%-20s min %7lld  mean %7lld  max %7lld ns  (%d CTAs)\n", names[s], mn, sum / cnt, mx, cnt);
+  }
+  printf("CTA 0:"); for (int s = 0; s < 11; ++s) printf(" %lld", h[s] ? h[s] - t0 : -1); printf("\n");
+  return 0;
+}
+#endif
+
 const char* cgp_last_error(void) { return g_err; }
 
 const char* cgp_status_string(int s) {
@@ -770,7 +926,9 @@ const char* cgp_kernel_family(const cgp_kernel_desc* d, int32_t N, int32_t M, in
   if (which < 2) {  // Kuf
     const bool bwd = which == 1;
     if (f32) {
-      const int fam = opt(bwd ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 2);
+      int fam = opt(bwd ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 3);
+      if (!bwd && fam == 3 && umma16_kuf_plan(d, g, mode, M, nullptr)) return "umma16";
+      if (fam == 3) fam = 2;
       if (fam == 2 && umma_ok(d, g, mode, M) &&
           umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total <= 227 * 1024 && (!bwd || g.P > umma::TN))
         return "umma32";
@@ -779,10 +937,12 @@ const char* cgp_kernel_family(const cgp_kernel_desc* d, int32_t N, int32_t M, in
     return opt(bwd ? g_opt.kuf_bwd : g_opt.kuf_fwd, 1) ? "dmma64" : "scalar";
   }
   const bool bwd = which == 3;
-  if (kdiag_saved_ok(d, g, mode)) return f32 ? "umma32" : (bwd ? "saved-row-sums" : "dmma64");
+  if (kdiag_saved_ok(d, g, mode))
+    return bwd ? "saved-row-sums" : (f32 ? (kdiag_fwd_f32_family(d, g, mode) == 3 ? "umma16" : "umma32") : "dmma64");
   if (f32) {
-    const int fam = opt(bwd ? g_opt.kdiag_bwd_f32 : g_opt.kdiag_fwd_f32, 2);
-    if (fam == 2 && umma_ok(d, g, mode, 0)) return "umma32";
+    if (!bwd && kdiag_fwd_f32_family(d, g, mode) == 3) return "umma16";
+    const int fam = opt(bwd ? g_opt.kdiag_bwd_f32 : g_opt.kdiag_fwd_f32, 3);
+    if (fam >= 2 && umma_ok(d, g, mode, 0)) return "umma32";
     return fam ? "hmma32" : "scalar";
   }
   return opt(bwd ? g_opt.kdiag_bwd : g_opt.kdiag_fwd, 1) ? "dmma64" : "scalar";
