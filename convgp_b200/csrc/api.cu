@@ -382,8 +382,8 @@ static int run_umma16_kuf_fwd(const cgp_kernel_desc* d, const Geo& g, int N, int
 #ifdef CGP_UMMA_TRACE
   {
     static long long* tr = nullptr;
-    if (!tr) { cudaMalloc(&tr, 256 * 16 * sizeof(long long)); }
-    cudaMemsetAsync(tr, 0, 256 * 16 * sizeof(long long), st);
+    if (!tr) { cudaMalloc(&tr, 8192 * sizeof(long long)); }
+    cudaMemsetAsync(tr, 0, 8192 * sizeof(long long), st);
     p.trace = tr;
     g_umma16_trace = tr;
   }
@@ -441,6 +441,15 @@ static int run_umma16_kdiag(const cgp_kernel_desc* d, const Geo& g, int N, const
     for (int j = i; j < p.nt; ++j) p.cost_img += j == p.nt - 1 ? p.NL / 64 : 2;
   p.Pn = (float)g.P;
   if (N < 1) return CGP_OK;
+#ifdef CGP_UMMA_TRACE
+  {
+    static long long* tr = nullptr;
+    if (!tr) { cudaMalloc(&tr, 8192 * sizeof(long long)); }
+    cudaMemsetAsync(tr, 0, 8192 * sizeof(long long), st);
+    p.trace = tr;
+    g_umma16_trace = tr;
+  }
+#endif
   const size_t smem = umma16::kd_smem_plan(umma16::pad_kd(g.D), d->H * d->W * d->C, p.Rpad, nbuf).total;
   const long long units = (long long)N * p.nt * (p.nt + 1) / 2;
   const long long grid = std::max<long long>(1, std::min<long long>(units, num_sms()));
@@ -457,7 +466,7 @@ static int run_umma16_kdiag(const cgp_kernel_desc* d, const Geo& g, int N, const
         cur = smem;                                                                                           \
       }                                                                                                       \
     }                                                                                                         \
-    kernel<<<(unsigned)grid, umma16::kThreads, smem, st>>>(p);                                                \
+    kernel<<<(unsigned)grid, umma16::kdThreads, smem, st>>>(p);                                               \
     CGP_CUDA_CHECK(cudaGetLastError());                                                                       \
     return CGP_OK;                                                                                            \
   }
@@ -868,7 +877,7 @@ int cgp_umma_trace_dump(void) {
 // development only: %globaltimer stamps of every CTA of the last umma16 launch, ns after the first CTA's entry
 int cgp_umma16_trace_dump(void) {
   if (!g_umma16_trace) return 0;
-  static long long h[256 * 16];
+  static long long h[8192];
   cudaDeviceSynchronize();
   cudaMemcpy(h, g_umma16_trace, sizeof(h), cudaMemcpyDeviceToHost);
   long long t0 = 0;
@@ -882,6 +891,19 @@ int cgp_umma16_trace_dump(void) {
     if (cnt) printf("%-20s min %7lld  mean %7lld  max %7lld ns  (%d CTAs)\n", names[s], mn, sum / cnt, mx, cnt);
   }
   printf("CTA 0:"); for (int s = 0; s < 11; ++s) printf(" %lld", h[s] ? h[s] - t0 : -1); printf("\n");
+  printf("per CTA (units: ns from first acc to last unit):");
+  for (int b = 0; b < 256; ++b) if (h[b * 16 + 11]) printf(" %lld:%lld", h[b * 16 + 11], h[b * 16 + 8] - h[b * 16 + 7]);
+  printf("\n");
+  long long c0 = 0;
+  for (int i = 4096; i < 8192; ++i) if (h[i] && (!c0 || h[i] < c0)) c0 = h[i];
+  for (int u = 0; u < 64; ++u) {
+    bool any = false;
+    for (int s = 0; s < 8; ++s) any |= h[4096 + u * 8 + s] != 0;
+    if (!any) break;
+    printf("unit %2d:", u);
+    for (int s = 0; s < 8; ++s) printf(" %7lld", h[4096 + u * 8 + s] ? h[4096 + u * 8 + s] - c0 : -1);
+    printf("\n");
+  }
   return 0;
 }
 #endif

@@ -114,8 +114,14 @@ constexpr uint32_t kOneLo = 0x00003C00u;  // (1.0, 0) as (term 1 | term 2 << 16)
       p.trace[(size_t)blockIdx.x * 16 + (slot)] = (long long)gt_;           \
     }                                                                       \
   } while (0)
+// per-unit clock64 stamps of CTA 0: trace[4096 + u * 8 + slot]
+#define CGP_TU(slot, u)                                                                       \
+  do {                                                                                        \
+    if (p.trace && blockIdx.x == 0 && (u) < 64) p.trace[4096 + (u) * 8 + (slot)] = clock64(); \
+  } while (0)
 #else
 #define CGP_T16(slot) do { } while (0)
+#define CGP_TU(slot, u) do { } while (0)
 #endif
 
 // One operand row of KP slots, each a packed (term 1 | term 2 << 16) pair, into the K-major no-swizzle UMMA layout
@@ -492,8 +498,12 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
 // which is 204 800 exps per 576-patch image against 368 640 for the full Gram in 128-row tiles (umma32.cuh).
 // Per image the row sums r[q], v = sum_q w_q r[q] (Kdiag itself) and v2 = sum w w k * exponent are what the backward
 // needs (api.cu: cgp_kdiag_fwd_saved / cgp_kdiag_bwd_saved); `save` may be null (plain forward).
-// Warps: 0-6 producers, 7 issuer, 8-15 epilogue (TMEM lane quarter = warp % 4, column half = (warp - 8) / 4);
-// four TMEM accumulators of 128 columns.
+// Warps (512 threads): 0-6 producers, 7 issuer, 8-15 epilogue (TMEM lane quarter = warp % 4, column half = (warp - 8) / 4:
+// 64 columns of a unit, 32 of a last-column unit); four TMEM accumulators of 128 columns.  Units run column tile by
+// column tile (j outer, i = 0 ... j), so a thread keeps the weighted column sums of its columns in registers across
+// the mirrored units of a column tile and the transpose-reduce over the rows runs once per column tile.  The kernel is
+// bound by instruction issue (7 per pair + the per-unit hand-offs), not by MUFU: hence few, wide epilogue warps.
+constexpr int kdThreads = 512;
 constexpr int kdProd = 224;
 constexpr int kdIssuerWarp = 7;
 constexpr int kdEpiWarp0 = 8;
@@ -514,6 +524,7 @@ struct KdParams {
   int nbuf;  // image buffers (1 or 2)
   int cost_img;  // cost of one image: 2 per 128-column unit, NL / 64 per last-column unit
   float Pn;
+  long long* trace;  // development only (CGP_UMMA_TRACE builds)
 };
 
 struct KdSmem {
@@ -541,7 +552,7 @@ __host__ __device__ inline KdSmem kd_smem_plan(int KD, int HWC, int Rpad, int nb
   s.cacc = o;  // [4 lane quarters][Rpad] column sums of the mirrored tiles
   o += 4 * Rpad * 4;
   s.red = o;
-  o += 64;
+  o += 128;
   s.bars = o;
   o += 256;
   s.total = o;
@@ -549,7 +560,7 @@ __host__ __device__ inline KdSmem kd_smem_plan(int KD, int HWC, int Rpad, int nb
 }
 
 template <int PH, int PW>
-__global__ void __launch_bounds__(kThreads, 1) kdiag_fwd_kernel(const KdParams p) {
+__global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams p) {
   constexpr int D = PH * PW;
   constexpr int KD = pad_kd(D);
   constexpr int KS = KD / 16;
@@ -578,6 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) kdiag_fwd_kernel(const KdParams p
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) CGP_T16(0);
   // work split by cost: CTA b owns the units whose first cost unit lies in [total b / B, total (b + 1) / B)
   const long long total = (long long)p.N * p.cost_img;
   const long long clo = total * blockIdx.x / gridDim.x, chi = total * (blockIdx.x + 1) / gridDim.x;
@@ -600,24 +612,24 @@ __global__ void __launch_bounds__(kThreads, 1) kdiag_fwd_kernel(const KdParams p
         ++nun;
       }
       c += unit_cost(j);
-      if (++j == nt) {
-        if (++i == nt) {
-          i = 0;
+      if (++i > j) {  // column tile by column tile: (0, j) ... (j, j)
+        i = 0;
+        if (++j == nt) {
+          j = 0;
           ++n;
         }
-        j = i;
       }
     }
   }
 
-  for (int i = tid; i < Rpad; i += kThreads) {
+  for (int i = tid; i < Rpad; i += kdThreads) {
     const int q = min(i, p.P - 1);
     const int c = q / p.Pc, pos = q % p.Pc;
     w[i] = i < p.P ? (p.Wt ? p.Wt[i] : 1.f) : 0.f;
     org[i] = ((pos / p.Wout) * p.Wd + (pos % p.Wout)) * p.C + c;
   }
-  for (int i = tid; i < 2 * Rpad; i += kThreads) racc[i] = racc2[i] = 0.f;
-  for (int i = tid; i < 4 * Rpad; i += kThreads) cacc[i] = 0.f;
+  for (int i = tid; i < 2 * Rpad; i += kdThreads) racc[i] = racc2[i] = 0.f;
+  for (int i = tid; i < 4 * Rpad; i += kdThreads) cacc[i] = 0.f;
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&img_full[b], kdProd / 32);
@@ -640,6 +652,7 @@ __global__ void __launch_bounds__(kThreads, 1) kdiag_fwd_kernel(const KdParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
+  if (tid == 0) CGP_T16(1);
 
   const float lsv = p.ls[0], sig2 = p.var[0];
   const float c2 = 1.4426950408889634f / (2.f * lsv * lsv);
@@ -666,9 +679,9 @@ __global__ void __launch_bounds__(kThreads, 1) kdiag_fwd_kernel(const KdParams p
       int i = i_first, j = j_first;
       for (int u = 0; u < nun; ++u) {
         if (u == 0 || (i == 0 && j == 0)) ++n_imgs;
-        if (++j == nt) {
-          if (++i == nt) i = 0;
-          j = i;
+        if (++i > j) {
+          i = 0;
+          if (++j == nt) j = 0;
         }
       }
     }
@@ -722,7 +735,9 @@ __global__ void __launch_bounds__(kThreads, 1) kdiag_fwd_kernel(const KdParams p
           ++k;
           mbar_wait(&img_full[k % p.nbuf], (k / p.nbuf) & 1);
         }
+        CGP_TU(0, u);
         if (u >= 4) mbar_wait(&acc_empty[u & 3], ((u >> 2) - 1) & 1);
+        CGP_TU(1, u);
         tc_fence_after();
         const uint64_t db = d0 + (uint64_t)(((k % p.nbuf) * IMG_BYTES) >> 4);
         const uint64_t da = db + (uint64_t)((i * TM * 16) >> 4), dbj = db + (uint64_t)((j * 128 * 16) >> 4);
@@ -736,11 +751,12 @@ __global__ void __launch_bounds__(kThreads, 1) kdiag_fwd_kernel(const KdParams p
           mma_f16_ss(dcol, da + o, dbj + o, idesc, 1);
         }
         mma_commit(&acc_full[u & 3]);
+        CGP_TU(2, u);
         const bool last_of_image = (i == nt - 1 && j == nt - 1) || u + 1 == nun;
         if (last_of_image) mma_commit(&img_empty[k % p.nbuf]);
-        if (++j == nt) {
-          if (++i == nt) i = 0;
-          j = i;
+        if (++i > j) {
+          i = 0;
+          if (++j == nt) j = 0;
         }
       }
     }
@@ -752,7 +768,7 @@ __global__ void __launch_bounds__(kThreads, 1) kdiag_fwd_kernel(const KdParams p
     const int row = quarter * 32 + lane;
     const float P2 = p.Pn * p.Pn, s_kd = sig2 / P2;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    auto epi_sum = [&](float v) -> float {
+    auto epi_sum = [&](float v) -> float {  // combine the epilogue warps in a fixed order -> every thread
       v = warp_sum(v);
       named_sync(2, kdEpi);
       if (lane == 0) red[ew] = v;
@@ -762,16 +778,16 @@ __global__ void __launch_bounds__(kThreads, 1) kdiag_fwd_kernel(const KdParams p
     auto flush_image = [&](int n) {
       named_sync(2, kdEpi);
       float v1 = 0.f, v2 = 0.f;
-      for (int q = et; q < p.P; q += kdEpi) {
+      for (int q = et; q < Rpad; q += kdEpi) {
         const float r = (racc[q] + racc[Rpad + q]) + ((cacc[q] + cacc[Rpad + q]) + (cacc[2 * Rpad + q] + cacc[3 * Rpad + q]));
         const float r2 = racc2[q] + racc2[Rpad + q];
-        v1 = fmaf(w[q], r, v1);
-        v2 = fmaf(w[q], r2, v2);
-        if (p.save) atomicAdd(p.save + (size_t)n * p.P + q, r);  // an image can be shared by two CTAs
-      }
-      for (int q = et; q < Rpad; q += kdEpi) {
         racc[q] = racc[Rpad + q] = racc2[q] = racc2[Rpad + q] = 0.f;
         cacc[q] = cacc[Rpad + q] = cacc[2 * Rpad + q] = cacc[3 * Rpad + q] = 0.f;
+        if (q < p.P) {
+          v1 = fmaf(w[q], r, v1);
+          v2 = fmaf(w[q], r2, v2);
+          if (p.save) atomicAdd(p.save + (size_t)n * p.P + q, r);  // an image can be shared by two CTAs
+        }
       }
       const float v = epi_sum(v1);
       const float vv = epi_sum(v2);
@@ -783,64 +799,96 @@ __global__ void __launch_bounds__(kThreads, 1) kdiag_fwd_kernel(const KdParams p
         }
       }
     };
+    // weighted column sums of this thread's row over the mirrored units of the current column tile
+    float csa[32], csb[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) csa[t] = csb[t] = 0.f;
+    bool cs_dirty = false;
     int n = n_first, i = i_first, j = j_first, k = 0;
     for (int u = 0; u < nun; ++u) {
       const float* en = en0 + (k & 3) * Rpad;
-      const bool last_col = j == nt - 1, mirrored = j > i;
-      const int cw = last_col ? p.NL / 2 : 64;  // this warp's columns of the unit: 32 or 64
+      const bool wide = j != nt - 1 || p.NL == 128, mirrored = j > i;
+      const int cw = wide ? 64 : 32;            // this warp's columns of the unit
       const int c0 = j * 128 + half * cw;       // first patch column
       const int rg = i * TM + row;              // this thread's patch row
+      if (et == 0) CGP_TU(3, u);
       mbar_wait(&acc_full[u & 3], (u >> 2) & 1);
+      if (et == 0) CGP_TU(4, u);
+      if (et == 0 && u == 0) CGP_T16(7);
       tc_fence_after();
       const float eq = en[rg], wq = w[rg];  // (the norms of the image are visible once its first MMA has completed)
+      const float wm = mirrored ? wq : 0.f;
       const uint32_t taddr = lane_base + (uint32_t)(u & 3) * 128 + (uint32_t)(half * cw);
-      uint32_t va[32], vb[32];
-      tmem_ld32(taddr, va);
-      if (cw == 64) tmem_ld32(taddr + 32, vb);
-      tmem_wait_ld(va);
-      if (cw == 64) tmem_wait_ld(vb);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[u & 3]);
       float acc1 = 0.f, acc2 = 0.f;
-      auto chunk = [&](uint32_t (&v)[32], int cc) {
+      uint32_t v[32];
+      auto chunk = [&](float (&cs)[32], int cc) {
         const float4* w4 = reinterpret_cast<const float4*>(w + cc);
         const float4* e4 = reinterpret_cast<const float4*>(en + cc);
-        float cs[32];
+#ifndef CGP_KD_ABLATE
+#define CGP_KD_ABLATE 0
+#endif
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 wv = w4[q], ev = e4[q];
           const float ww[4] = {wv.x, wv.y, wv.z, wv.w}, ee[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float arg = (__uint_as_float(v[4 * q + t]) + eq) + ee[t];
-            const float kk = ex2f(arg);
+            const float arg = (CGP_KD_ABLATE & 8) ? __uint_as_float(v[4 * q + t]) + ee[t] : (__uint_as_float(v[4 * q + t]) + eq) + ee[t];
+            const float kk = (CGP_KD_ABLATE & 4) ? arg : ex2f(arg);
             const float a = ww[t] * kk;
             acc1 += a;
-            acc2 = fmaf(a, arg, acc2);
-            cs[4 * q + t] = wq * kk;
+            if (!(CGP_KD_ABLATE & 2)) acc2 = fmaf(a, arg, acc2);
+            if (!(CGP_KD_ABLATE & 1)) cs[4 * q + t] = fmaf(wm, kk, cs[4 * q + t]);
           }
         }
-        if (mirrored) {  // warp-uniform
-          const float colsum = umma::warp_column_sums(cs, lane);
-          cacc[quarter * Rpad + cc + lane] += colsum;  // owner-exclusive: (lane quarter, column)
-        }
       };
-      chunk(va, c0);
-      if (cw == 64) chunk(vb, c0 + 32);
+      tmem_ld32(taddr, v);
+      tmem_wait_ld(v);
+      if (!wide) {  // warp-uniform: a single 32-column chunk
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[u & 3]);
+      }
+      if (et == 0) CGP_TU(5, u);
+      chunk(csa, c0);
+      if (wide) {
+        tmem_ld32(taddr + 32, v);
+        tmem_wait_ld(v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[u & 3]);
+        chunk(csb, c0 + 32);
+      }
+      cs_dirty |= mirrored;
+      if (et == 0) CGP_TU(6, u);
+      if (et == 255) CGP_TU(7, u);
       racc[half * Rpad + rg] += acc1;  // owner-exclusive: (row, column half)
       racc2[half * Rpad + rg] += mirrored ? 2.f * acc2 : acc2;
-      if (++j == nt) {
-        if (++i == nt) {
-          i = 0;
+      const bool end_of_tile = i == j || u + 1 == nun;
+      if (end_of_tile && cs_dirty) {  // warp-uniform: the column tile (or this CTA's part of it) is complete
+        // lane L: column c0 + L (then c0 + 32 + L) summed over this warp's 32 rows; owner-exclusive (lane quarter, column)
+        cacc[quarter * Rpad + c0 + lane] += umma::warp_column_sums(csa, lane);
+        if (wide) cacc[quarter * Rpad + c0 + 32 + lane] += umma::warp_column_sums(csb, lane);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) csa[t] = csb[t] = 0.f;
+        cs_dirty = false;
+      }
+      if (++i > j) {
+        i = 0;
+        if (++j == nt) {
+          j = 0;
           flush_image(n);
           ++n;
           ++k;
         }
-        j = i;
       }
     }
+    if (et == 0) CGP_T16(8);
     if (nun > 0 && !(i == 0 && j == 0)) flush_image(n);
+    if (et == 0) {
+      CGP_T16(9);
+      if (p.trace) p.trace[(size_t)blockIdx.x * 16 + 11] = nun;
+    }
   }
 
   tc_fence_before();

@@ -22,7 +22,7 @@ ap.add_argument("--reps", type=int, default=12)
 ap.add_argument("--cfg", default="cfg3")
 ap.add_argument("--images", type=int, default=0, help="minibatch size (default: the config's)")
 ap.add_argument("--lib", default="", help="load this copy of the library instead (tools/build_trace.sh)")
-ap.add_argument("--trace", action="store_true", help="dump the umma16 time stamps of the last Kuf forward launch")
+ap.add_argument("--trace", default="", help="kuf_fwd | kdiag_fwd | kuf_bwd: dump the umma16 time stamps of one launch of it")
 ap.add_argument("--randw", action="store_true", help="patch weights ~ N(0, 1) instead of ones")
 a = ap.parse_args()
 if a.lib:
@@ -92,6 +92,6 @@ for name, fn in fns.items():
 print(out)
 if a.trace:
     import ctypes
-    fns["kuf_fwd"]()
+    fns[a.trace]()
     torch.cuda.synchronize()
     ctypes.CDLL(_lib.LIB_PATH).cgp_umma16_trace_dump()
