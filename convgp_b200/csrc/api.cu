@@ -411,6 +411,64 @@ static int run_umma16_kuf_fwd(const cgp_kernel_desc* d, const Geo& g, int N, int
 #undef CALL
 }
 
+// Kuf backward (umma16.cuh kuf_bwd_kernel): one (row tile, patch tile) pair and a range of images per CTA.
+static bool umma16_bwd_plan(const cgp_kernel_desc* d, const Geo& g, int mode) {
+  if (mode != 1 || d->dtype != CGP_F32 || d->out_mode == CGP_OUT_PER_CHANNEL) return false;
+  constexpr int TN = 192;
+  const int n_pt = (g.P + TN - 1) / TN;
+  return g.D + 2 <= 32 &&
+         umma16::bwd_smem_plan(umma16::pad_k(g.D), TN, d->H * d->W * d->C, n_pt * TN).total <= 227 * 1024;
+}
+
+static int run_umma16_kuf_bwd(const cgp_kernel_desc* d, const Geo& g, int N, int M, const void* X, const void* Z,
+                              const void* W, const void* var, const void* ls, const void* G, void* dZ, void* dW,
+                              void* dvar, void* dls, cudaStream_t st) {
+  constexpr int TN = 192;
+  umma16::BwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
+  p.ls = (const float*)ls; p.G = (const float*)G; p.dZ = (float*)dZ; p.dW = W ? (float*)dW : nullptr;
+  p.dvar = (float*)dvar; p.dls = (float*)dls;
+  p.N = N; p.M = M; p.H = d->H; p.Wd = d->W; p.C = d->C; p.Wout = g.Wout; p.Pc = g.Pc; p.P = g.P;
+  p.n_pt = (g.P + TN - 1) / TN;
+  p.n_zt = (M + umma16::TM - 1) / umma16::TM;
+  p.n_rp = (p.n_zt + 1) / 2;
+  const int pairs = p.n_pt * p.n_rp;
+  p.S = std::max(1, std::min(N, num_sms() / pairs));
+  p.Pn = (float)g.P;
+  if (N < 1 || M < 1) return CGP_OK;
+#ifdef CGP_UMMA_TRACE
+  {
+    static long long* tr = nullptr;
+    if (!tr) { cudaMalloc(&tr, 8192 * sizeof(long long)); }
+    cudaMemsetAsync(tr, 0, 8192 * sizeof(long long), st);
+    p.trace = tr;
+    g_umma16_trace = tr;
+  }
+#endif
+  const size_t smem = umma16::bwd_smem_plan(umma16::pad_k(g.D), TN, d->H * d->W * d->C, p.n_pt * TN).total;
+  const unsigned grid = (unsigned)(pairs * p.S);
+  int dev = 0;
+  CGP_CUDA_CHECK(cudaGetDevice(&dev));
+#define CALL(PH_, PW_)                                                                                        \
+  {                                                                                                           \
+    void (*kernel)(const umma16::BwdParams) = umma16::kuf_bwd_kernel<PH_, PW_, TN>;                           \
+    {                                                                                                         \
+      std::lock_guard<std::mutex> lk(g_launch_mu);                                                            \
+      size_t& cur = g_launch_smem[std::make_pair((const void*)kernel, dev)];                                  \
+      if (smem > cur) {                                                                                       \
+        CGP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        cur = smem;                                                                                           \
+      }                                                                                                       \
+    }                                                                                                         \
+    kernel<<<grid, umma16::kbThreads, smem, st>>>(p);                                                         \
+    CGP_CUDA_CHECK(cudaGetLastError());                                                                       \
+    return CGP_OK;                                                                                            \
+  }
+  CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+#undef CALL
+}
+
 // Kdiag forward (umma16.cuh kdiag_fwd_kernel): one pairing domain per image, tiles on or above the diagonal only.
 static bool umma16_kdiag_plan(const cgp_kernel_desc* d, const Geo& g, int mode, int* nbuf_out) {
   if (mode != 1 || d->dtype != CGP_F32 || d->out_mode == CGP_OUT_PER_CHANNEL) return false;
@@ -554,6 +612,8 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
     int fam = opt(BWD ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 3);  // 3 umma16 | 2 umma32 | 1 hmma32 | 0 scalar
     if (!BWD && fam == 3 && umma16_kuf_plan(d, g, mode, M, nullptr))
       return run_umma16_kuf_fwd(d, g, N, M, X, Z, W, var, ls, out, st);
+    if (BWD && fam == 3 && umma16_bwd_plan(d, g, mode))
+      return run_umma16_kuf_bwd(d, g, N, M, X, Z, W, var, ls, G, dZ, dW, dvar, dls, st);
     if (fam == 3) fam = 2;
     if (fam == 2 && umma_ok(d, g, mode, M) &&
         umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total <= 227 * 1024) {
@@ -950,6 +1010,7 @@ const char* cgp_kernel_family(const cgp_kernel_desc* d, int32_t N, int32_t M, in
     if (f32) {
       int fam = opt(bwd ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 3);
       if (!bwd && fam == 3 && umma16_kuf_plan(d, g, mode, M, nullptr)) return "umma16";
+      if (bwd && fam == 3 && umma16_bwd_plan(d, g, mode)) return "umma16";
       if (fam == 3) fam = 2;
       if (fam == 2 && umma_ok(d, g, mode, M) &&
           umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total <= 227 * 1024 && (!bwd || g.P > umma::TN))

@@ -898,5 +898,580 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
   }
 }
 
+
+// ------------------------------------------------------------------------------------ Kuf backward
+// dZ, dW, dvariance, dlengthscale of Kuf from G = dL/dKuf in one kernel (closed forms: SURVEY.md 8a), flash-attention
+// shaped like umma32's kuf_dz_kernel but organised so that the epilogue does only what no GEMM can do:
+//   * a CTA owns up to TWO inducing row tiles (A of GEMM1, two fp16 terms, resident in shared memory), ONE patch tile
+//     j and a contiguous range of images; a unit is (image, row tile), the two units of an image share its staged
+//     operands;
+//   * GEMM1  S = Z . X^T (6 kind::f16 MMAs, both operands in shared memory, norms in the spare inner slots);
+//   * epilogue (12 warps, 16 columns at a time): c0 = G[m, n] / P * ex2(S), cf = c0 w_p -> two fp16 terms c1 + c2
+//     written back over S in TMEM.  dW needs the sum of c0 over rows AND images: the columns of a CTA never change, so
+//     every thread keeps its rows' 64 partial column sums in registers for the CTA's whole life (one FADD per pair) and
+//     the transpose-reduce over the rows runs ONCE per CTA;
+//   * GEMM2  acc += cf . B^T with B = sqrt(2 c2) [x_p | .] | 1 | |x_p|^2 as two fp16 terms (kind::f16, A = c1 / c2 from
+//     TMEM; the data rows are the image's packed fp16 pairs as GEMM1 uses them).  Accumulator columns:
+//       d < D: sum_p cf x_p[d]     D: sum_p cf     D + 1: sum_p cf |x_p|^2
+//     from which dZ = var / l^2 (acc_d - z_d acc_D), dvariance = sum acc_D and -- because the exponent is
+//     S = c2 (2 z.x - |z|^2 - |x|^2) -- dlengthscale's sum_p cf S = c2 (2 z.acc - |z|^2 acc_D - acc_{D+1}) all come out
+//     of the SAME rounded coefficients, with no per-pair instruction.
+// Per pair the epilogue issues ex2, two FMULs, one FADD and the three-instruction fp16 split: MUFU-bound (8 cycles per
+// warp-pair on the MUFU pipe); the tensor pipe carries 576 + 1536 cycles per 128 x 192 unit.
+// Warps (512 threads): 0-11 epilogue (TMEM lane quarter = warp % 4, column third = warp / 4), 12-14 producers, 15 issuer.
+// Warp order = scheduling priority (higher warp ids win the issue slot): the issuer's few instructions are
+// latency-critical, the producers feed it, the instruction-heavy epilogue takes what is left.
+// (Warps are allocated four at a time: 17-20 warps would leave 96 registers per thread, and the epilogue's 64 column
+// sums need the 128 of a 16-warp CTA.)
+constexpr int kbThreads = 512;
+constexpr int kbProd = 96;
+constexpr int kbEpi = 384;
+constexpr int kbProdWarp0 = 12;
+constexpr int kbIssuerWarp = 15;
+constexpr int kbEpiWarp0 = 0;
+
+struct BwdParams {
+  const float* X;
+  const float* Z;
+  const float* Wt;
+  const float* var;
+  const float* ls;
+  const float* G;  // dL/dKuf (M, N)
+  float* dZ;
+  float* dW;
+  float* dvar;
+  float* dls;
+  int N, M, H, Wd, C, Wout, Pc, P;
+  int n_pt, n_zt, n_rp, S;  // patch tiles, row tiles, row-tile pairs, image shares per (row-tile pair, patch tile)
+  float Pn;
+  long long* trace;
+};
+
+struct BwdSmem {
+  int sZ, sB, sBt, raw, xs, en, w, org, cacc, red, bars, total;
+};
+__host__ __device__ inline BwdSmem bwd_smem_plan(int KP, int TN, int HWC, int Ppad) {
+  BwdSmem s;
+  int o = 0;
+  s.sZ = o;  // two row tiles
+  o += 2 * TM * KP * 4;
+  s.sB = o;  // 2 slots of GEMM1's patch tile
+  o += 2 * TN * KP * 4;
+  s.sBt = o;  // 3 slots of GEMM2's operand: 64 rows (two terms of 32 output columns) x TN patches, fp16
+  o += 3 * 64 * TN * 2;
+  s.raw = o;
+  o += 3 * al16(HWC * 4);
+  s.xs = o;
+  o += 2 * al16(HWC * 4);
+  s.en = o;  // per image: |x_q|^2 of the tile's patches (two-deep)
+  o += 2 * TN * 4;
+  s.w = o;
+  o += al16(Ppad * 4);
+  s.org = o;
+  o += al16(Ppad * 4);
+  s.cacc = o;  // [4 lane quarters][TN] column sums at the end
+  o += 4 * TN * 4;
+  s.red = o;  // 32 floats of reduction scratch, then the octet table
+  o += 128 + (TN / 8) * 4 + 32;
+  s.bars = o;
+  o += 256;
+  s.total = o;
+  return s;
+}
+
+__device__ __forceinline__ void mma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+      "r"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};\n" ::"r"(v[0]),
+      "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(taddr)
+      : "memory");
+}
+
+template <int PH, int PW, int TN>
+__global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p) {
+  constexpr int D = PH * PW;
+  constexpr int KP = pad_k(D);
+  constexpr int KS = KP / 16;
+  constexpr int CW = TN / 3;
+  static_assert(CW == 64 && D + 2 <= 32, "tile columns / GEMM2 output columns");
+  constexpr uint32_t B_TILE = TN * KP * 4, B_TERM = TN * KP * 2, BT_SLOT = 64 * TN * 2, Z_TILE = TM * KP * 4;
+  constexpr uint32_t kTmemAcc = 2 * TN;  // TMEM: S0 | S1 | acc of row tile 0 (64 columns) | acc of row tile 1
+  static_assert(2 * TN + 128 <= 512, "TMEM budget");
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int HWC = p.H * p.Wd * p.C;
+  const int Ppad = p.n_pt * TN;
+  const BwdSmem L = bwd_smem_plan(KP, TN, HWC, Ppad);
+  unsigned char* sZ = smem + L.sZ;
+  unsigned char* sB = smem + L.sB;
+  unsigned char* sBt = smem + L.sBt;
+  float* raw0 = reinterpret_cast<float*>(smem + L.raw);
+  const int raw_stride = al16(HWC * 4) / 4;
+  uint32_t* xs0 = reinterpret_cast<uint32_t*>(smem + L.xs);
+  float* en0 = reinterpret_cast<float*>(smem + L.en);
+  float* w = reinterpret_cast<float*>(smem + L.w);
+  int* org = reinterpret_cast<int*>(smem + L.org);
+  float* cacc = reinterpret_cast<float*>(smem + L.cacc);
+  float* red = reinterpret_cast<float*>(smem + L.red);
+  int* oct_ok = reinterpret_cast<int*>(smem + L.red) + 32;  // [TN / 8] octet = eight consecutive pixels of one patch row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* staged = bars;          // [2] producers -> issuer: GEMM1's patch tile of an image
+  uint64_t* b_free = bars + 2;      // [2] every GEMM1 of the image is complete: its patch-tile slot is reusable
+  uint64_t* g1_done = bars + 4;     // [2] GEMM1 of a unit complete: S readable
+  uint64_t* coef_ready = bars + 6;  // [2] epilogue wrote the coefficients of a unit
+  uint64_t* staged_t = bars + 8;    // [3] producers -> issuer: GEMM2's operand of an image
+  uint64_t* bt_free = bars + 11;    // [3] every GEMM2 of the image is complete
+  uint64_t* img_bar = bars + 14;    // [3] cp.async ring
+  uint64_t* z_ready = bars + 17;
+  uint64_t* all_done = bars + 18;
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = blockIdx.x / p.S, share = blockIdx.x % p.S;
+  const int rp = grp / p.n_pt, jt = grp % p.n_pt;  // row-tile pair, patch tile
+  const int nrt = min(2, p.n_zt - 2 * rp);         // row tiles of this CTA
+  const int n_lo = (int)((long long)p.N * share / p.S), n_hi = (int)((long long)p.N * (share + 1) / p.S);
+  const int nimg = n_hi - n_lo, nun = nimg * nrt;
+  const int m0 = 2 * rp * TM, c0p = jt * TN;  // first inducing row, first patch column
+
+  for (int i = tid; i < Ppad; i += kbThreads) {
+    const int q = min(i, p.P - 1);
+    const int c = q / p.Pc, pos = q % p.Pc;
+    w[i] = i < p.P ? (p.Wt ? p.Wt[i] : 1.f) : 0.f;
+    org[i] = ((pos / p.Wout) * p.Wd + (pos % p.Wout)) * p.C + c;
+  }
+  // (integer divisions only here: in the unit loop their I2F / MUFU.RCP / F2I would queue behind the epilogue's ex2)
+  for (int o = tid; o < TN / 8; o += kbThreads) {
+    const int g0 = c0p + o * 8;
+    oct_ok[o] = g0 + 8 <= p.P && (g0 % p.Pc) % p.Wout + 8 <= p.Wout;
+  }
+  // GEMM2's operand: zero rows for the unused output columns, and row D (term 1) = ones, written once
+  for (int i = tid; i < (int)(3 * BT_SLOT / 4); i += kbThreads) {
+    const int r = (4 * i) % 1024;  // byte inside the 64-row x 16-byte block of one patch octet
+    reinterpret_cast<uint32_t*>(sBt)[i] = (r / 128 == (D >> 3) && (r % 128) / 16 == (D & 7)) ? 0x3C003C00u : 0u;
+  }
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&staged[b], kbProd / 32);
+      mbar_init(&b_free[b], 1);
+      mbar_init(&g1_done[b], 1);
+      mbar_init(&coef_ready[b], kbEpi / 32);
+    }
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(&staged_t[b], kbProd / 32);
+      mbar_init(&bt_free[b], 1);
+      mbar_init(&img_bar[b], kbProd);
+    }
+    mbar_init(z_ready, 8);
+    mbar_init(all_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kbIssuerWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+
+  const float lsv = p.ls[0], sig2 = p.var[0];
+  const float c2 = 1.4426950408889634f / (2.f * lsv * lsv);
+  const float sc = sqrtf(2.f * c2);
+  const int si = p.Wd * p.C, sj = p.C;
+
+  if (warp >= kbProdWarp0 && warp < kbIssuerWarp) {
+    // ============================== producers (one pass per image)
+    const int pt = tid - kbProdWarp0 * 32;
+    const bool x16 = (reinterpret_cast<uintptr_t>(p.X) & 15) == 0 && (HWC & 3) == 0;
+    auto fetch_image = [&](int n, int k) {
+      const float* src = p.X + (size_t)n * HWC;
+      float* dst = raw0 + (k % 3) * raw_stride;
+      if (x16)
+        for (int i = pt; i < HWC / 4; i += kbProd) umma::cp_async16(dst + 4 * i, src + 4 * i);
+      else
+        for (int i = pt; i < HWC; i += kbProd) umma::cp_async4(dst + i, src + i);
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&img_bar[k % 3])) : "memory");
+    };
+    if (nimg > 0) fetch_image(n_lo, 0);
+    uint32_t oct_mask = 0;
+    for (int o = 0; o < TN / 8; ++o) oct_mask |= oct_ok[o] ? (1u << o) : 0u;
+    for (int k = 0; k < nimg; ++k) {
+      if (pt == 0) CGP_TU(0, k);
+      if (k + 1 < nimg) fetch_image(n_lo + k + 1, k + 1);  // buffer (k + 1) % 3 held image k - 2
+      mbar_wait(&img_bar[k % 3], (k / 3) & 1);
+      if (pt == 0) CGP_TU(1, k);
+      const float* raw = raw0 + (k % 3) * raw_stride;
+      uint32_t* xs = xs0 + (k & 1) * raw_stride;
+      float* en = en0 + (k & 1) * TN;
+      for (int i0 = pt; i0 < HWC; i0 += 4 * kbProd) {  // four pixels in flight per thread
+        float x[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) x[t] = i0 + t * kbProd < HWC ? raw[i0 + t * kbProd] : 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (i0 + t * kbProd < HWC) xs[i0 + t * kbProd] = split_f16(x[t] * sc);
+      }
+      {
+        constexpr int kPerQ = (TN + kbProd - 1) / kbProd;
+        float ss[kPerQ];
+        const float* base[kPerQ];
+#pragma unroll
+        for (int t = 0; t < kPerQ; ++t) {
+          ss[t] = 0.f;
+          base[t] = raw + org[c0p + min(pt + t * kbProd, TN - 1)];
+        }
+#pragma unroll
+        for (int a = 0; a < PH; ++a)
+#pragma unroll
+          for (int b = 0; b < PW; ++b)
+#pragma unroll
+            for (int t = 0; t < kPerQ; ++t) ss[t] = fmaf(base[t][a * si + b * sj], base[t][a * si + b * sj], ss[t]);
+#pragma unroll
+        for (int t = 0; t < kPerQ; ++t)
+          if (pt + t * kbProd < TN) en[pt + t * kbProd] = ss[t];
+      }
+      named_sync(1, kbProd);
+      // ---- GEMM1's patch tile
+      if (k >= 2) mbar_wait(&b_free[k & 1], ((k >> 1) - 1) & 1);
+      {
+        unsigned char* buf = sB + (k & 1) * B_TILE;
+        // (shared-memory operations queue behind the epilogue's MUFU stream: every loop of the producers is unrolled so
+        // that the loads of all its iterations are in flight together)
+#pragma unroll
+        for (int rr = 0; rr < (TN + kbProd - 1) / kbProd; ++rr) {
+          const int r = pt + rr * kbProd;
+          if (r >= TN) break;
+          const int o = org[c0p + r];
+          uint32_t v[KP];
+#pragma unroll
+          for (int a = 0; a < PH; ++a)
+#pragma unroll
+            for (int b = 0; b < PW; ++b) v[a * PW + b] = xs[o + a * si + b * sj];
+          uint32_t f3;
+          const uint32_t f12 = split3_f16(-c2 * en[r], f3);
+          v[D] = kOneLo;
+          v[D + 1] = f12;
+          v[D + 2] = kOneLo;
+          v[D + 3] = f3 & 0xFFFFu;
+#pragma unroll
+          for (int d = D + 4; d < KP; ++d) v[d] = 0u;
+          put_row<KP>(buf, TN, r, v);
+        }
+      }
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&staged[k & 1]);
+      if (pt == 0) CGP_TU(2, k);
+      // ---- GEMM2's operand: rows d (term 1) and 32 + d (term 2), 16-byte chunks of 8 consecutive patches.  Data
+      // rows are the packed fp16 pairs of the image (scaled by sqrt(2 c2): undone at the end); row D + 1 = |x_p|^2
+      if (k >= 3) mbar_wait(&bt_free[k % 3], ((k / 3) - 1) & 1);
+      {
+        unsigned char* bt = sBt + (k % 3) * BT_SLOT;
+        auto put8 = [&](const uint32_t (&hp)[8], int oct, int d) {
+          uint4 t1, t2;
+          t1.x = prmt(hp[0], hp[1], 0x5410); t1.y = prmt(hp[2], hp[3], 0x5410);
+          t1.z = prmt(hp[4], hp[5], 0x5410); t1.w = prmt(hp[6], hp[7], 0x5410);
+          t2.x = prmt(hp[0], hp[1], 0x7632); t2.y = prmt(hp[2], hp[3], 0x7632);
+          t2.z = prmt(hp[4], hp[5], 0x7632); t2.w = prmt(hp[6], hp[7], 0x7632);
+          const int off = oct * (16 * 64) + (d >> 3) * 128 + (d & 7) * 16;
+          *reinterpret_cast<uint4*>(bt + off) = t1;
+          *reinterpret_cast<uint4*>(bt + off + 4 * 128) = t2;
+        };
+        constexpr int kItems = (TN / 8) * D, kPer = (kItems + kbProd - 1) / kbProd;
+        const uint32_t* srcs[kPer];
+        int step[kPer], dsts[kPer];
+#pragma unroll
+        for (int ii = 0; ii < kPer; ++ii) {  // all origin lookups first
+          const int item = min(pt + ii * kbProd, kItems - 1);
+          const int d = item % D, oct = item / D;
+          const int doff = (d / PW) * si + (d % PW) * sj;
+          const int g0 = c0p + oct * 8;
+          const bool ok = (oct_mask >> oct) & 1u;  // eight consecutive real patches of one patch row
+          srcs[ii] = xs + org[g0] + doff;
+          step[ii] = ok ? sj : 0;
+          dsts[ii] = ok ? oct * 256 + d : -(oct * 256 + d) - 1;
+        }
+#pragma unroll
+        for (int ii = 0; ii < kPer; ++ii) {
+          if (pt + ii * kbProd >= kItems) break;
+          uint32_t hp[8];
+          const int code = dsts[ii] < 0 ? -dsts[ii] - 1 : dsts[ii];
+          const int oct = code >> 8, d = code & 255;
+          if (dsts[ii] >= 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hp[e] = srcs[ii][e * step[ii]];
+          } else {
+            const int doff = (d / PW) * si + (d % PW) * sj;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hp[e] = xs[org[c0p + oct * 8 + e] + doff];
+          }
+          put8(hp, oct, d);
+        }
+        for (int oct = pt; oct < TN / 8; oct += kbProd) {
+          uint32_t hp[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) hp[e] = split_f16(en[oct * 8 + e]);
+          put8(hp, oct, D + 1);
+        }
+      }
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&staged_t[k % 3]);
+      if (pt == 0) CGP_TU(3, k);
+    }
+    umma::cp_async_wait_all();
+  } else if (warp == kbIssuerWarp) {
+    // ============================== MMA issuer
+    if (lane == 0 && nun > 0) {
+      constexpr uint32_t id1 = make_idesc(TM, TN, umma::kFmtF16);
+      constexpr uint32_t id2a = make_idesc(TM, 64, umma::kFmtF16), id2b = make_idesc(TM, 32, umma::kFmtF16);
+      const uint64_t da0 = make_desc(smem_u32(sZ), 16 * TM, 128);
+      const uint64_t db0 = make_desc(smem_u32(sB), 16 * TN, 128);
+      const uint64_t dbt0 = make_desc(smem_u32(sBt), 16 * 64, 128);
+      const uint64_t a_term = (uint64_t)((2 * KP * TM) >> 4), b_term = (uint64_t)(B_TERM >> 4);
+      auto gemm2 = [&](int u) {
+        const int k = nrt == 2 ? u >> 1 : u, rt = u - k * nrt;
+        if (rt == 0) mbar_wait(&staged_t[k % 3], (k / 3) & 1);
+        mbar_wait(&coef_ready[u & 1], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sbuf = tmem_base + (uint32_t)(u & 1) * TN;
+        const uint32_t dacc = tmem_base + kTmemAcc + (uint32_t)rt * 64;
+        const uint64_t dbt = dbt0 + (uint64_t)((k % 3) * (BT_SLOT >> 4));
+#pragma unroll
+        for (int g = 0; g < TN / 16; ++g) {  // 16 patches per step: c1 in packed columns 16 g ... + 7, c2 in + 8 ... + 15
+          const uint64_t db = dbt + (uint64_t)((2 * g) * ((16 * 64) >> 4));
+          mma_f16_ts(dacc, sbuf + 16 * g, db, id2a, (k | g) != 0);  // c1 . [B1 | B2]
+          mma_f16_ts(dacc, sbuf + 16 * g + 8, db, id2b, 1);         // c2 . B1
+        }
+        if (rt == nrt - 1) mma_commit(&bt_free[k % 3]);
+        if (u == nun - 1) mma_commit(all_done);
+        CGP_TU(5, u);
+      };
+      mbar_wait(z_ready, 0);
+      for (int u = 0; u < nun; ++u) {
+        const int k = nrt == 2 ? u >> 1 : u, rt = u - k * nrt;
+        if (rt == 0) mbar_wait(&staged[k & 1], (k >> 1) & 1);
+        tc_fence_after();
+        // the S buffer (u & 1) was last read by GEMM2(u - 2), which precedes this in issue order
+        const uint64_t da = da0 + (uint64_t)((rt * Z_TILE) >> 4);
+        const uint64_t db = db0 + (uint64_t)(((k & 1) * B_TILE) >> 4);
+        const uint32_t dcol = tmem_base + (uint32_t)(u & 1) * TN;
+#pragma unroll
+        for (int s2 = 0; s2 < KS; ++s2) {
+          const uint64_t oa = (uint64_t)((s2 * 2 * 16 * TM) >> 4), ob = (uint64_t)((s2 * 2 * 16 * TN) >> 4);
+          mma_f16_ss(dcol, da + a_term + oa, db + ob, id1, s2 > 0);
+          mma_f16_ss(dcol, da + oa, db + b_term + ob, id1, 1);
+          mma_f16_ss(dcol, da + oa, db + ob, id1, 1);
+        }
+        mma_commit(&g1_done[u & 1]);
+        if (rt == nrt - 1) mma_commit(&b_free[k & 1]);
+        CGP_TU(4, u);
+        if (u >= 1) gemm2(u - 1);
+      }
+      gemm2(nun - 1);
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue
+    const int ew = warp - kbEpiWarp0, et = tid - kbEpiWarp0 * 32;
+    const int quarter = warp & 3, third = ew >> 2;
+    const int row = quarter * 32 + lane;
+    // the row tiles: scaled rows, norms, two fp16 terms (third t stages row tile t, one row per thread)
+    const int mz = m0 + third * TM + row;  // the row this thread stages (third < nrt) and finalises
+    float znorm = 0.f;                     // c2 |z|^2 of that row
+    if (third < 2) {
+      uint32_t v[KP];
+#pragma unroll
+      for (int d = 0; d < KP; ++d) v[d] = 0u;
+      if (third < nrt && mz < p.M) {
+        const float* z = p.Z + (size_t)mz * D;
+        float ss = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float x = z[d];
+          ss = fmaf(x, x, ss);
+          v[d] = split_f16(x * sc);
+        }
+        znorm = c2 * ss;
+        uint32_t e3;
+        v[D] = split3_f16(-znorm, e3);
+        v[D + 1] = kOneLo;
+        v[D + 2] = e3 & 0xFFFFu;
+        v[D + 3] = kOneLo;
+      }
+      put_row<KP>(sZ + third * Z_TILE, TM, row, v);
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(z_ready);
+    }
+    const int ma = m0 + row, mb = m0 + TM + row;  // this thread's rows in the two row tiles
+    const bool va = ma < p.M, vb = nrt > 1 && mb < p.M;
+    // fp16 needs a scale: a power of two, uniform over the CTA (the dW column sums add rows), chosen so that the
+    // largest possible |cf| = max |G| max |w| / P lands at 2^14; everything is unscaled once at the end
+    float cscale = 1.f, inv_cscale = 1.f;
+    {
+      float gm = 0.f, wm = 0.f;
+      for (int n = n_lo + third; n < n_hi; n += 3) {
+        if (va) gm = fmaxf(gm, fabsf(p.G[(size_t)ma * p.N + n]));
+        if (vb) gm = fmaxf(gm, fabsf(p.G[(size_t)mb * p.N + n]));
+      }
+      for (int i = et; i < TN; i += kbEpi) wm = fmaxf(wm, fabsf(w[c0p + i]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+        wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+      }
+      if (lane == 0) {
+        red[ew] = gm;
+        red[16 + ew] = wm;
+      }
+      named_sync(2, kbEpi);
+      gm = wm = 0.f;
+#pragma unroll
+      for (int k2 = 0; k2 < kbEpi / 32; ++k2) {
+        gm = fmaxf(gm, red[k2]);
+        wm = fmaxf(wm, red[16 + k2]);
+      }
+      named_sync(2, kbEpi);
+      const float t = gm * wm / p.Pn;
+      if (t > 0.f && t < 3.0e38f) {
+        const int e = min(max(14 - (ilogbf(t) + 1), -100), 100);
+        cscale = exp2f((float)e);
+        inv_cscale = exp2f((float)-e);
+      }
+    }
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float gs = cscale / p.Pn;
+    const float4* wt4 = reinterpret_cast<const float4*>(w + c0p + third * CW);
+    float dwacc[CW];  // these rows' sum over the CTA's images of c0, for each of this warp's 64 columns
+#pragma unroll
+    for (int t = 0; t < CW; ++t) dwacc[t] = 0.f;
+    float ga = (nun > 0 && va) ? p.G[(size_t)ma * p.N + n_lo] : 0.f;
+    float gb = (nun > 0 && vb) ? p.G[(size_t)mb * p.N + n_lo] : 0.f;
+    for (int u = 0; u < nun; ++u) {
+      const int k = nrt == 2 ? u >> 1 : u, rt = u - k * nrt;
+      const float Gm = (rt == 0 ? ga : gb) * gs;
+      if (rt == nrt - 1 && k + 1 < nimg) {  // next image's upstream gradients, a unit ahead
+        if (va) ga = p.G[(size_t)ma * p.N + n_lo + k + 1];
+        if (vb) gb = p.G[(size_t)mb * p.N + n_lo + k + 1];
+      }
+      mbar_wait(&g1_done[u & 1], (u >> 1) & 1);
+      if (et == 0) CGP_TU(6, u);
+      tc_fence_after();
+      const uint32_t tbuf = lane_addr + (uint32_t)(u & 1) * TN + (uint32_t)(third * CW);
+#pragma unroll
+      for (int g = 0; g < CW / 16; ++g) {
+        uint32_t v[16];
+        tmem_ld16(tbuf + 16 * g, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                       "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                     :
+                     : "memory");
+        uint32_t cp[16];  // c1 pairs in [0, 8), the residuals c2 in [8, 16)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 wq = wt4[4 * g + q];
+          const float ww[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float a0 = Gm * ex2f(__uint_as_float(v[4 * q + 2 * h])), a1 = Gm * ex2f(__uint_as_float(v[4 * q + 2 * h + 1]));
+            dwacc[16 * g + 4 * q + 2 * h] += a0;
+            dwacc[16 * g + 4 * q + 2 * h + 1] += a1;
+            const float f0 = a0 * ww[2 * h], f1 = a1 * ww[2 * h + 1];
+            const uint32_t c1 = umma::pack_f16x2(f1, f0);
+            cp[2 * q + h] = c1;
+            cp[8 + 2 * q + h] = umma::pack_f16x2(f1 - umma::f16_hi_to_f32(c1), f0 - umma::f16_lo_to_f32(c1));
+          }
+        }
+        tmem_st16(tbuf + 16 * g, cp);  // both terms go back into the 16 columns this group just vacated
+      }
+      umma::tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&coef_ready[u & 1]);
+      if (et == 0) CGP_TU(7, u);
+    }
+    // ---- the CTA's units are complete
+    if (nun > 0) {
+      mbar_wait(all_done, 0);
+      tc_fence_after();
+    }
+    // dW: transpose-reduce the register column sums over the warp's rows, then over the four lane quarters
+    // (rows past M carry G = 0, i.e. exact zeros)
+    if (p.dW && nun > 0) {
+      float a[32], b[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        a[t] = dwacc[t];
+        b[t] = dwacc[32 + t];
+      }
+      cacc[quarter * TN + third * CW + lane] = umma::warp_column_sums(a, lane);
+      cacc[quarter * TN + third * CW + 32 + lane] = umma::warp_column_sums(b, lane);
+      named_sync(2, kbEpi);
+      for (int c = et; c < TN; c += kbEpi) {
+        const float v = (cacc[c] + cacc[TN + c]) + (cacc[2 * TN + c] + cacc[3 * TN + c]);
+        if (c0p + c < p.P) atomicAdd(p.dW + c0p + c, sig2 * inv_cscale * v);
+      }
+    }
+    float s0row = 0.f, slrow = 0.f;
+    if (third < nrt && nun > 0) {  // warp-uniform: tcgen05.ld is a warp-collective; third t finalises row tile t
+      uint32_t d1[32], d2[32];
+      tmem_ld32(lane_addr + kTmemAcc + third * 64, d1);
+      tmem_ld32(lane_addr + kTmemAcc + third * 64 + 32, d2);
+      tmem_wait_ld(d1);
+      tmem_wait_ld(d2);
+      if (mz < p.M) {
+        const float* zr = p.Z + (size_t)mz * D;
+        s0row = (__uint_as_float(d1[D]) + __uint_as_float(d2[D])) * inv_cscale;
+        const float qv = (__uint_as_float(d1[D + 1]) + __uint_as_float(d2[D + 1])) * inv_cscale;
+        const float scz = sig2 / (lsv * lsv), unsc = inv_cscale / sc;  // the data rows carried sqrt(2 c2) x
+        float zdot = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float dz = (__uint_as_float(d1[d]) + __uint_as_float(d2[d])) * unsc;
+          const float zd = zr[d];
+          zdot = fmaf(zd, dz, zdot);
+          if (p.dZ) atomicAdd(p.dZ + (size_t)mz * D + d, scz * (dz - zd * s0row));
+        }
+        slrow = 2.f * c2 * zdot - znorm * s0row - c2 * qv;  // sum_p cf S, S in log2 units
+      }
+    }
+    {
+      const float t0 = warp_sum(s0row), t2 = warp_sum(slrow);
+      named_sync(2, kbEpi);
+      if (lane == 0) {
+        red[ew] = t0;
+        red[16 + ew] = t2;
+      }
+      named_sync(2, kbEpi);
+      if (et == 0) {
+        float a0 = 0.f, a2 = 0.f;
+        for (int k2 = 0; k2 < kbEpi / 32; ++k2) {
+          a0 += red[k2];
+          a2 += red[16 + k2];
+        }
+        if (p.dvar) atomicAdd(p.dvar, a0);
+        if (p.dls) atomicAdd(p.dls, -2.f * sig2 / lsv * a2 / 1.4426950408889634f);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kbIssuerWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 }  // namespace umma16
 }  // namespace cgp
