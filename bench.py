@@ -407,17 +407,18 @@ def bound_fn(cfg, dtype_name, peaks):
                                  "this GPU by cgp_peak_probe (MEASURED_PEAKS.json has no FP64 figure)")
 
     # float32 runs on three pipes at once: the contraction FMAs (2D of the 2D+2G / 2D+8G flops of a pair, 4D of the
-    # 4D+8G of a Kuf backward pair) on tcgen05 tensor cores at three TF32 MMAs per float32 product, the exps on MUFU,
-    # everything else on the FP32 FMA pipe.  The slowest of the three bounds the kernel.
+    # 4D+8G of a Kuf backward pair) on tcgen05 tensor cores at three kind::f16 MMAs per float32 product (two fp16 terms
+    # per operand, umma16.cuh; kind::f16 runs at twice the probed kind::tf32 rate), the exps on MUFU, everything else on
+    # the FP32 FMA pipe.  The slowest of the three bounds the kernel.
     def t_bound(fl, ex):
         pairs = ex / cfg.G
         per_pair = fl / pairs
         contraction = pairs * (4 * D if per_pair > 3 * D + 4 * cfg.G else 2 * D)
-        return max(3 * (contraction / 2) / peaks["tcgen05_tf32"], ex / peaks["mufu_ex2"],
+        return max(3 * (contraction / 2) / (2 * peaks["tcgen05_tf32"]), ex / peaks["mufu_ex2"],
                    (fl - contraction) / (2 * peaks["fp32_fma"]))
-    return t_bound, "mufu", ("max(3 * contraction FMAs / tcgen05 kind::tf32 rate, exps / MUFU ex2 rate, remaining flops / "
-                             "(2 * FFMA rate)): the three pipes run concurrently; MUFU binds at this shape.  All rates "
-                             "probed on this GPU by cgp_peak_probe")
+    return t_bound, "mufu", ("max(3 * contraction FMAs / tcgen05 kind::f16 rate (= 2 x the probed kind::tf32 rate), exps / "
+                             "MUFU ex2 rate, remaining flops / (2 * FFMA rate)): the three pipes run concurrently; MUFU "
+                             "binds at this shape.  All rates probed on this GPU by cgp_peak_probe")
 
 
 def step_bound(cfg, dtype_name, peaks, n_images, executed_only=False, kd_saved=True):

@@ -163,6 +163,18 @@ __device__ __forceinline__ void put_row(unsigned char* buf, int R, int r, const 
 
 __host__ __device__ inline int al16(int bytes) { return (bytes + 15) / 16 * 16; }
 
+// One image -> shared memory with cp.async, completion on an mbarrier (count = nthreads): every calling thread copies
+// its pieces and arrives when they have landed.
+__device__ __forceinline__ void fetch_image_async(float* dst, const float* src, int n_floats, int t, int nthreads,
+                                                  uint64_t* bar) {
+  const bool x16 = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (n_floats & 3) == 0;
+  if (x16)
+    for (int i = t; i < n_floats / 4; i += nthreads) umma::cp_async16(dst + 4 * i, src + 4 * i);
+  else
+    for (int i = t; i < n_floats; i += nthreads) umma::cp_async4(dst + i, src + i);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ------------------------------------------------------------------------------------ Kuf forward
 struct KufSmem {
   int sZ, sB, raw, xs, en, w, org, racc, bars, total;
@@ -234,15 +246,21 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
   const int n0 = (int)(lo / per_img);
   const int j0 = (int)((lo % per_img) / p.n_zt), i0 = (int)(lo % p.n_zt);
   if (tid == 0) CGP_T16(0);
-  // warm the TLB / L2 for everything the start-up reads, before the prologue: the first touches cost microseconds
-  {
+  // The first image is requested before anything else (its first touch costs microseconds on a cold L2 / TLB): the
+  // barriers of the image ring are initialised ahead of the rest of the prologue, which then overlaps the fetch.
+  if (tid == 0) {
+    for (int b = 0; b < 3; ++b) mbar_init(&img_bar[b], kProd);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp < kProd / 32 && nun > 0)
+    fetch_image_async(raw0, p.X + (size_t)n0 * (p.H * p.Wd * p.C), p.H * p.Wd * p.C, tid, kProd, &img_bar[0]);
+  {  // warm the L2 for the inducing patches too
     const char* zb = reinterpret_cast<const char*>(p.Z);
     const int zbytes = p.M * D * 4;
     for (int o = tid * 128; o < zbytes; o += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(zb + o));
-    const char* xb = reinterpret_cast<const char*>(p.X + (size_t)n0 * (p.H * p.Wd * p.C));
-    const int xbytes = min(2, p.N - n0) * p.H * p.Wd * p.C * 4;
-    for (int o = tid * 128; o < xbytes; o += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + o));
   }
+  const float lsv = p.ls[0], sig2 = p.var[0];
 
   for (int i = tid; i < Ppad; i += kThreads) {
     const int q = min(i, p.P - 1);  // rows past the last patch repeat it (finite exponents); their weight is zero
@@ -260,7 +278,6 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], kEpi / 32);
     }
-    for (int b = 0; b < 3; ++b) mbar_init(&img_bar[b], kProd);
     mbar_init(z_ready, kEpi / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -276,7 +293,6 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
   const uint32_t tmem_base = *tmem_base_s;
   if (tid == 0) CGP_T16(1);
 
-  const float lsv = p.ls[0], sig2 = p.var[0];
   const float c2 = 1.4426950408889634f / (2.f * lsv * lsv);
   const float sc = sqrtf(2.f * c2);  // data slots carry sqrt(2 c2) * value on both sides
   const int si = p.Wd * p.C, sj = p.C;  // image strides of a patch's rows / columns
@@ -284,17 +300,9 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
   if (warp < kProd / 32) {
     // ============================== producers: images -> packed fp16 pairs -> patch tiles
     const int pt = tid;
-    const bool x16 = (reinterpret_cast<uintptr_t>(p.X) & 15) == 0 && (HWC & 3) == 0;
     auto fetch_image = [&](int n, int k) {
-      const float* src = p.X + (size_t)n * HWC;
-      float* dst = raw0 + (k % 3) * raw_stride;
-      if (x16)
-        for (int i = pt; i < HWC / 4; i += kProd) umma::cp_async16(dst + 4 * i, src + 4 * i);
-      else
-        for (int i = pt; i < HWC; i += kProd) umma::cp_async4(dst + i, src + i);
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&img_bar[k % 3])) : "memory");
+      fetch_image_async(raw0 + (k % 3) * raw_stride, p.X + (size_t)n * HWC, HWC, pt, kProd, &img_bar[k % 3]);
     };
-    if (nun > 0) fetch_image(n0, 0);
     int n = n0, j = j0, ki = -1, cur = -1;
     int u = 0, tile = 0;
     while (u < nun) {
@@ -643,6 +651,15 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
     }
   }
 
+  // the first image is requested before the rest of the prologue (see kuf_fwd_kernel)
+  if (tid == 0) {
+    for (int b = 0; b < 3; ++b) mbar_init(&img_bar[b], kdProd);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp < kdProd / 32 && nun > 0)
+    fetch_image_async(raw0, p.X + (size_t)n_first * HWC, HWC, tid, kdProd, &img_bar[0]);
+  const float lsv = p.ls[0], sig2 = p.var[0];
   for (int i = tid; i < Rpad; i += kdThreads) {
     const int q = min(i, p.P - 1);
     const int c = q / p.Pc, pos = q % p.Pc;
@@ -660,7 +677,6 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], kdEpi / 32);
     }
-    for (int b = 0; b < 3; ++b) mbar_init(&img_bar[b], kdProd);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kdIssuerWarp) {
@@ -675,7 +691,6 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
   const uint32_t tmem_base = *tmem_base_s;
   if (tid == 0) CGP_T16(1);
 
-  const float lsv = p.ls[0], sig2 = p.var[0];
   const float c2 = 1.4426950408889634f / (2.f * lsv * lsv);
   const float sc = sqrtf(2.f * c2);
   const int si = p.Wd * p.C, sj = p.C;
@@ -684,15 +699,8 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
   if (warp < kdProd / 32) {
     // ============================== producers: one image -> every patch row, once
     const int pt = tid;
-    const bool x16 = (reinterpret_cast<uintptr_t>(p.X) & 15) == 0 && (HWC & 3) == 0;
     auto fetch_image = [&](int n, int k) {
-      const float* src = p.X + (size_t)n * HWC;
-      float* dst = raw0 + (k % 3) * raw_stride;
-      if (x16)
-        for (int i = pt; i < HWC / 4; i += kdProd) umma::cp_async16(dst + 4 * i, src + 4 * i);
-      else
-        for (int i = pt; i < HWC; i += kdProd) umma::cp_async4(dst + i, src + i);
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&img_bar[k % 3])) : "memory");
+      fetch_image_async(raw0 + (k % 3) * raw_stride, p.X + (size_t)n * HWC, HWC, pt, kdProd, &img_bar[k % 3]);
     };
     // number of images: walk the units
     int n_imgs = 0;
@@ -706,7 +714,6 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
         }
       }
     }
-    if (n_imgs > 0) fetch_image(n_first, 0);
     for (int k = 0; k < n_imgs; ++k) {
       const int n = n_first + k;
       if (k + 1 < n_imgs) fetch_image(n + 1, k + 1);
@@ -1061,6 +1068,15 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
   const int nimg = n_hi - n_lo, nun = nimg * nrt;
   const int m0 = 2 * rp * TM, c0p = jt * TN;  // first inducing row, first patch column
 
+  // the first image is requested before the rest of the prologue (see kuf_fwd_kernel)
+  if (tid == 0) {
+    for (int b = 0; b < 3; ++b) mbar_init(&img_bar[b], kbProd);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp >= kbProdWarp0 && warp < kbIssuerWarp && nimg > 0)
+    fetch_image_async(raw0, p.X + (size_t)n_lo * HWC, HWC, tid - kbProdWarp0 * 32, kbProd, &img_bar[0]);
+  const float lsv = p.ls[0], sig2 = p.var[0];
   for (int i = tid; i < Ppad; i += kbThreads) {
     const int q = min(i, p.P - 1);
     const int c = q / p.Pc, pos = q % p.Pc;
@@ -1087,7 +1103,6 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
     for (int b = 0; b < 3; ++b) {
       mbar_init(&staged_t[b], kbProd / 32);
       mbar_init(&bt_free[b], 1);
-      mbar_init(&img_bar[b], kbProd);
     }
     mbar_init(z_ready, 8);
     mbar_init(all_done, 1);
@@ -1104,7 +1119,6 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_s;
 
-  const float lsv = p.ls[0], sig2 = p.var[0];
   const float c2 = 1.4426950408889634f / (2.f * lsv * lsv);
   const float sc = sqrtf(2.f * c2);
   const int si = p.Wd * p.C, sj = p.C;
@@ -1112,17 +1126,9 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
   if (warp >= kbProdWarp0 && warp < kbIssuerWarp) {
     // ============================== producers (one pass per image)
     const int pt = tid - kbProdWarp0 * 32;
-    const bool x16 = (reinterpret_cast<uintptr_t>(p.X) & 15) == 0 && (HWC & 3) == 0;
     auto fetch_image = [&](int n, int k) {
-      const float* src = p.X + (size_t)n * HWC;
-      float* dst = raw0 + (k % 3) * raw_stride;
-      if (x16)
-        for (int i = pt; i < HWC / 4; i += kbProd) umma::cp_async16(dst + 4 * i, src + 4 * i);
-      else
-        for (int i = pt; i < HWC; i += kbProd) umma::cp_async4(dst + i, src + i);
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&img_bar[k % 3])) : "memory");
+      fetch_image_async(raw0 + (k % 3) * raw_stride, p.X + (size_t)n * HWC, HWC, pt, kbProd, &img_bar[k % 3]);
     };
-    if (nimg > 0) fetch_image(n_lo, 0);
     uint32_t oct_mask = 0;
     for (int o = 0; o < TN / 8; ++o) oct_mask |= oct_ok[o] ? (1u << o) : 0u;
     for (int k = 0; k < nimg; ++k) {

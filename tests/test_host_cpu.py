@@ -171,8 +171,16 @@ def test_options_api_and_family_query():
     f32 = _lib.Spec(torch.float32, 28, 28, 1, 5, 5, 0, 0, 1, False, False)
     gen = _lib.Spec(torch.float64, 28, 28, 1, 4, 4, 0, 0, 1, False, False)
     assert L.cgp_kernel_family(f64.ref(), 200, 750, 0) == b"dmma64"
-    assert L.cgp_kernel_family(f32.ref(), 200, 750, 0) == b"umma32"
-    assert L.cgp_kernel_family(f32.ref(), 200, 750, 1) == b"umma32"
+    for which in (0, 1, 2):  # Kuf forward / backward, Kdiag forward: the two-fp16-term tcgen05 family by default
+        assert L.cgp_kernel_family(f32.ref(), 200, 750, which) == b"umma16"
+    _lib.set_option("kuf_fwd_f32", 2)
+    _lib.set_option("kuf_bwd_f32", 2)
+    try:
+        assert L.cgp_kernel_family(f32.ref(), 200, 750, 0) == b"umma32"
+        assert L.cgp_kernel_family(f32.ref(), 200, 750, 1) == b"umma32"
+    finally:
+        _lib.set_option("kuf_fwd_f32", -1)
+        _lib.set_option("kuf_bwd_f32", -1)
     assert L.cgp_kernel_family(gen.ref(), 200, 750, 2) == b"generic"
     _lib.set_option("kuf_fwd", 0)
     try:

@@ -29,7 +29,7 @@ STALL = "smsp__average_warps_issue_stalled_"
 out = ["# ncu --set full, %s: the six kernels of one hot-path step at config 3 (28x28, 5x5, M=750, N=200)\n" % TAG,
        "Recipe: `tools/profile_round.sh %s` (each ncu pass after a plain run of the same command exited 0):" % TAG,
        "`ncu --set full --clock-control none --import-source on -k regex:\"mma_kernel|kuu_fast|kdiag_bwd_saved\" -s 6 -c 6 "
-       "python tools/run_step.py --steps 3` and the same with `rowsum_kernel|kuf_dz_kernel|...` and `--dtype f32`.",
+       "python tools/run_step.py --steps 3` and the same with `kuf_fwd_kernel|kdiag_fwd_kernel|kuf_bwd_kernel|...` and `--dtype f32`.",
        "Raw exports: `%s_ncu_full_f64_raw.csv`, `%s_ncu_full_f32_raw.csv`; launch lists of the bench command: "
        "`%s_launches_bench_f64.csv`, `%s_launches_bench_f32.csv`; hottest source lines: `%s_hot_*.txt`." % ((TAG,) * 5),
        "DMMA and scalar FP64 share one physical pipe on B200 (`r1_probe_pipe_calibration.csv`), so \"FP64 pipe busy\" is "

@@ -2,13 +2,13 @@
 # Round-end profiling recipe (run on the GPU box through gpurun; every ncu pass follows a plain run of the same
 # command that exited 0).  Outputs under gpurun_out/, copied to profiles/ by hand.
 set -u
-T=${1:-r1z}
+T=${1:-r2}
 O=gpurun_out
 python tools/run_step.py --steps 2 || exit 1
 python tools/run_step.py --steps 2 --dtype f32 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:"mma_kernel|kuu_fast|kdiag_bwd_saved" -s 6 -c 6 \
     -o $O/${T}_f64 python tools/run_step.py --steps 3 > $O/${T}_ncu_f64.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"rowsum_kernel|kuf_dz_kernel|kuu_fast|kdiag_bwd_saved" -s 6 -c 6 \
+ncu --set full --clock-control none --import-source on -k regex:"kuf_fwd_kernel|kdiag_fwd_kernel|kuf_bwd_kernel|rowsum_kernel|kuf_dz_kernel|kuu_fast|kdiag_bwd_saved" -s 6 -c 6 \
     -o $O/${T}_f32 python tools/run_step.py --steps 3 --dtype f32 > $O/${T}_ncu_f32.log 2>&1
 for d in f64 f32; do
   ncu -i $O/${T}_$d.ncu-rep --page raw --csv > $O/${T}_ncu_full_${d}_raw.csv 2>/dev/null
