@@ -496,7 +496,7 @@ static int run_umma16_kdiag(const cgp_kernel_desc* d, const Geo& g, int N, const
   p.nbuf = nbuf;
   p.cost_img = 0;
   for (int i = 0; i < p.nt; ++i)
-    for (int j = i; j < p.nt; ++j) p.cost_img += j == p.nt - 1 ? p.NL / 64 : 2;
+    for (int j = i; j < p.nt; ++j) p.cost_img += (j == p.nt - 1 && p.NL == 64) ? 2 : 3;
   p.Pn = (float)g.P;
   if (N < 1) return CGP_OK;
 #ifdef CGP_UMMA_TRACE

@@ -551,7 +551,7 @@ struct KdParams {
   int NL;    // columns of the last column tile (64 or 128)
   int Rpad;  // 128 nt rows staged per image
   int nbuf;  // image buffers (1 or 2)
-  int cost_img;  // cost of one image: 2 per 128-column unit, NL / 64 per last-column unit
+  int cost_img;  // cost of one image: 3 per 128-column unit, 2 per 64-column unit
   float Pn;
   long long* trace;  // development only (CGP_UMMA_TRACE builds)
 };
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
   const long long total = (long long)p.N * p.cost_img;
   const long long clo = total * blockIdx.x / gridDim.x, chi = total * (blockIdx.x + 1) / gridDim.x;
   const int nt = p.nt;
-  auto unit_cost = [&](int j) { return j == nt - 1 ? p.NL / 64 : 2; };
+  auto unit_cost = [&](int j) { return j == nt - 1 && p.NL == 64 ? 2 : 3; };  // measured: 2 250 vs 1 500 cycles
   // first unit at or after cost `c` of the image-local scan
   int n_first = (int)(clo / p.cost_img), i_first = 0, j_first = 0, nun = 0;
   {

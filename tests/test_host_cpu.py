@@ -173,6 +173,12 @@ def test_options_api_and_family_query():
     assert L.cgp_kernel_family(f64.ref(), 200, 750, 0) == b"dmma64"
     for which in (0, 1, 2):  # Kuf forward / backward, Kdiag forward: the two-fp16-term tcgen05 family by default
         assert L.cgp_kernel_family(f32.ref(), 200, 750, which) == b"umma16"
+    # planar colour images (Conv with colour_channels = 3: one pairing domain) take the same family when the
+    # shared-memory plan fits; per-channel outputs and the colour-patch additive kernel do not
+    rgb = _lib.Spec(torch.float32, 16, 16, 3, 5, 5, _lib.LAYOUT_PLANAR, _lib.OUT_SUM, 1, False, False)
+    assert all(L.cgp_kernel_family(rgb.ref(), 30, 100, w) == b"umma16" for w in (0, 1, 2))
+    multi = _lib.Spec(torch.float32, 16, 16, 3, 5, 5, _lib.LAYOUT_PLANAR, _lib.OUT_PER_CHANNEL, 1, False, False)
+    assert L.cgp_kernel_family(multi.ref(), 30, 100, 0) != b"umma16"
     _lib.set_option("kuf_fwd_f32", 2)
     _lib.set_option("kuf_bwd_f32", 2)
     try:
