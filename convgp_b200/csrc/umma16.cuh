@@ -857,7 +857,8 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
 #endif
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 wv = w4[q], ev = e4[q];
+          const float4 wv = (CGP_KD_ABLATE & 16) ? make_float4(1.f, 1.f, 1.f, 1.f) : w4[q];
+          const float4 ev = (CGP_KD_ABLATE & 16) ? make_float4(0.f, 0.f, 0.f, 0.f) : e4[q];
           const float ww[4] = {wv.x, wv.y, wv.z, wv.w}, ee[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
