@@ -9,7 +9,7 @@ namespace cgp {
 constexpr int kChains = 8;
 
 template <int KIND>
-__global__ void __launch_bounds__(256) probe_kernel(int iters, double* sink, double seed) {
+__global__ void __launch_bounds__(384) probe_kernel(int iters, double* sink, double seed) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   __shared__ double tbl[kExpTable];
   if (KIND == 3) {
@@ -158,6 +158,27 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, double* sink, dou
 #pragma unroll
     for (int i = 0; i < kChains; ++i) s += a[i];
     if (s == 12345.678f) sink[0] = s;
+  } else if (KIND >= 18 && KIND <= 21) {  // MUFU ex2 with NF dependent-free FFMAs per ex2 (what an epilogue issues per pair)
+    constexpr int NF = KIND == 21 ? 2 : 6;
+    float a[kChains], acc[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+      a[i] = -(float)seed - i * 0.1f - tid * 1e-6f;
+      acc[i] = (float)i;
+    }
+    const float c1 = 1.0f + (float)seed * 1e-6f, c2 = (float)seed * 1e-7f;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+      for (int i = 0; i < kChains; ++i) {
+        const float k = Math<float>::exp_arg(a[i], nullptr);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) acc[i] = fmaf(acc[i], c1, f & 1 ? k : c2);
+        a[i] = -k;
+      }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i] + acc[i];
+    if (s == 12345.678f) sink[0] = s;
   } else if (KIND == 3) {  // library double exp
     double a[kChains];
 #pragma unroll
@@ -202,7 +223,9 @@ static int run_probe(double ops_per_thread_iter, double* result) {
   double* sink = nullptr;
   CGP_CUDA_CHECK(cudaMalloc(&sink, sizeof(double)));
   constexpr bool kOneWarp = KIND == 6 || KIND == 11 || KIND == 12 || KIND == 13;
-  const int blocks = kOneWarp ? num_sms() : num_sms() * 8, threads = kOneWarp ? 128 : 256;
+  // 19 / 20: two / three warps per sub-partition (the occupancy of an epilogue), one CTA per SM
+  const int blocks = (kOneWarp || KIND == 19 || KIND == 20) ? num_sms() : num_sms() * 8;
+  const int threads = kOneWarp ? 128 : (KIND == 19 ? 256 : (KIND == 20 ? 384 : 256));
   const int iters = (KIND == 3) ? 512 : (KIND >= 4 ? 1024 : 4096);
   cudaEvent_t e0, e1;
   CGP_CUDA_CHECK(cudaEventCreate(&e0));
@@ -324,6 +347,11 @@ extern "C" int cgp_peak_probe(int32_t kind, double* ops_per_s) {
     case 16: return run_probe<16>(kChains * 32.0, ops_per_s);
     // tcgen05.mma kind::tf32 (UMMA), FMAs per second
     case 17: return run_tcgen05_probe(ops_per_s);
+    // ex2 per second while six independent FFMAs are issued per ex2: 16 / 2 / 3 warps per sub-partition; 21: two FFMAs
+    case 18: return run_probe<18>(kChains, ops_per_s);
+    case 19: return run_probe<19>(kChains, ops_per_s);
+    case 20: return run_probe<20>(kChains, ops_per_s);
+    case 21: return run_probe<21>(kChains, ops_per_s);
     default:
       set_error("unknown probe kind %d", kind);
       return CGP_ERR_BAD_DESC;

@@ -130,7 +130,9 @@ int cgp_kfull_fwd(const cgp_kernel_desc* d, int32_t N, int32_t N2, const void* X
  * dependent-chain micro-kernel on the current device, synchronises, and returns operations per
  * second in *ops_per_s.  kind: 0 = FP64 FMA, 1 = FP32 FMA, 2 = MUFU ex2.approx.f32,
  * 3 = this library's double-precision exp, 4 = FP64 mma.sync m8n8k4 (counted as FMAs),
- * 16 = TF32 mma.sync m16n8k8, 17 = tcgen05.mma kind::tf32 (FMAs per second). */
+ * 16 = TF32 mma.sync m16n8k8, 17 = tcgen05.mma kind::tf32 (FMAs per second),
+ * 18 / 19 / 20 = ex2 per second while six FFMAs are issued per ex2 at 16 / 2 / 3 warps per sub-partition, 21 = with two
+ * FFMAs (what an exp-and-accumulate epilogue can sustain; other kinds: development probes, see csrc/probe.cu). */
 int cgp_peak_probe(int32_t kind, double* ops_per_s);
 
 /* Which hand-written CUDA kernel family a launch of this configuration dispatches to -- "dmma64" (FP64 warp MMA),
