@@ -349,49 +349,80 @@ static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int
 }
 
 // ---- float32 tcgen05 family, second generation (umma16.cuh): two fp16 terms per operand, both operands in shared
-// memory, nothing restaged per tile.  Planar layout with one RBF (fast mode 1), any channel count, summed output.
+// memory, nothing restaged per tile.  Summed output with
+//   fast mode 1: planar layout, one RBF over the patch, any channel count (all C P' patches are one pairing domain);
+//   fast mode 2: colour-patch layout with one RBF per channel (cifar.py:33-41): k = sum_g k_g where k_g only sees colour
+//                plane g of the image and elements g::C of an inducing patch, so the kernel is the SUM over g of the
+//                single-channel problem on plane g: one launch per group, accumulating into the same outputs.
+struct U16View {  // what one launch sees
+  int C, Cx, choff;   // staged channels, channels in memory, staged channel (C == 1 < Cx)
+  int P, Pc, D;       // patches of the pairing domain, positions per plane, elements per patch of the group
+  int zrow, zs, zo;   // Z[m * zrow + d * zs + zo]
+};
+static int u16_groups(const cgp_kernel_desc* d, int mode) { return mode == 2 ? d->C : 1; }
+static U16View u16_view(const cgp_kernel_desc* d, const Geo& g, int mode, int gi) {
+  U16View v;
+  if (mode == 2) {
+    v.C = 1; v.Cx = d->C; v.choff = gi; v.P = g.Pc; v.Pc = g.Pc; v.D = d->ph * d->pw;
+    v.zrow = g.D; v.zs = d->C; v.zo = gi;
+  } else {
+    v.C = d->C; v.Cx = d->C; v.choff = 0; v.P = g.P; v.Pc = g.Pc; v.D = g.D; v.zrow = g.D; v.zs = 1; v.zo = 0;
+  }
+  return v;
+}
+static bool u16_mode_ok(const cgp_kernel_desc* d, int mode) {
+  return (mode == 1 || mode == 2) && d->dtype == CGP_F32 && d->out_mode != CGP_OUT_PER_CHANNEL;
+}
+
 static bool umma16_kuf_plan(const cgp_kernel_desc* d, const Geo& g, int mode, int M, int* nbuf_out) {
-  if (mode != 1 || d->dtype != CGP_F32 || d->out_mode == CGP_OUT_PER_CHANNEL) return false;
-  const int KP = umma16::pad_k(g.D), TN = 192;
-  const int n_pt = (g.P + TN - 1) / TN, n_zt = (M + umma16::TM - 1) / umma16::TM;
+  if (!u16_mode_ok(d, mode)) return false;
+  const U16View v = u16_view(d, g, mode, 0);
+  const int KP = umma16::pad_k(v.D), TN = 192;
+  const int n_pt = (v.P + TN - 1) / TN, n_zt = (M + umma16::TM - 1) / umma16::TM;
   for (int nbuf = 3; nbuf >= 2; --nbuf)
-    if (umma16::kuf_smem_plan(KP, TN, d->H * d->W * d->C, n_pt * TN, n_zt * umma16::TM, nbuf).total <= 227 * 1024) {
+    if (umma16::kuf_smem_plan(KP, TN, d->H * d->W * v.C, n_pt * TN, n_zt * umma16::TM, nbuf).total <= 227 * 1024) {
       if (nbuf_out) *nbuf_out = nbuf;
       return true;
     }
   return false;
 }
 
-static int run_umma16_kuf_fwd(const cgp_kernel_desc* d, const Geo& g, int N, int M, const void* X, const void* Z,
-                              const void* W, const void* var, const void* ls, void* out, cudaStream_t st) {
+static int run_umma16_kuf_fwd(const cgp_kernel_desc* d, const Geo& g, int mode, int N, int M, const void* X,
+                              const void* Z, const void* W, const void* var, const void* ls, void* out,
+                              cudaStream_t st) {
   constexpr int TN = 192;
-  umma16::Params p;
-  memset(&p, 0, sizeof(p));
   int nbuf = 0;
-  if (!umma16_kuf_plan(d, g, 1, M, &nbuf)) { set_error("umma16 kuf: shared-memory plan does not fit"); return CGP_ERR_UNSUPPORTED; }
-  p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
-  p.ls = (const float*)ls; p.out = (float*)out;
-  p.N = N; p.M = M; p.H = d->H; p.Wd = d->W; p.C = d->C; p.Hout = g.Hout; p.Wout = g.Wout; p.Pc = g.Pc; p.P = g.P; p.D = g.D;
-  p.n_pt = (g.P + TN - 1) / TN;
-  p.n_zt = (M + umma16::TM - 1) / umma16::TM;
-  p.Mpad = p.n_zt * umma16::TM;
-  p.nbuf = nbuf;
-  p.n_units = (long long)N * p.n_pt * p.n_zt;
-  p.Pn = (float)g.P;
-  if (p.n_units < 1) return CGP_OK;
-#ifdef CGP_UMMA_TRACE
-  {
-    static long long* tr = nullptr;
-    if (!tr) { cudaMalloc(&tr, 8192 * sizeof(long long)); }
-    cudaMemsetAsync(tr, 0, 8192 * sizeof(long long), st);
-    p.trace = tr;
-    g_umma16_trace = tr;
-  }
-#endif
-  const size_t smem = umma16::kuf_smem_plan(umma16::pad_k(g.D), TN, d->H * d->W * d->C, p.n_pt * TN, p.Mpad, nbuf).total;
-  const long long grid = std::max<long long>(1, std::min<long long>(p.n_units, num_sms()));
+  if (!umma16_kuf_plan(d, g, mode, M, &nbuf)) { set_error("umma16 kuf: shared-memory plan does not fit"); return CGP_ERR_UNSUPPORTED; }
   int dev = 0;
   CGP_CUDA_CHECK(cudaGetDevice(&dev));
+  {  // one launch: CTA b works on RBF group b % G
+    const int G = u16_groups(d, mode);
+    const U16View v = u16_view(d, g, mode, 0);
+    umma16::Params p;
+    memset(&p, 0, sizeof(p));
+    p.G = G;
+    p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
+    p.ls = (const float*)ls; p.out = (float*)out;
+    p.N = N; p.M = M; p.H = d->H; p.Wd = d->W; p.C = v.C; p.Hout = g.Hout; p.Wout = g.Wout; p.Pc = v.Pc; p.P = v.P; p.D = v.D;
+    p.Cx = v.Cx; p.choff = v.choff; p.zrow = v.zrow; p.zs = v.zs; p.zo = v.zo;
+    p.n_pt = (v.P + TN - 1) / TN;
+    p.n_zt = (M + umma16::TM - 1) / umma16::TM;
+    p.Mpad = p.n_zt * umma16::TM;
+    p.nbuf = nbuf;
+    p.n_units = (long long)N * p.n_pt * p.n_zt;
+    p.Pn = (float)g.P;
+    if (p.n_units < 1) return CGP_OK;
+#ifdef CGP_UMMA_TRACE
+    {
+      static long long* tr = nullptr;
+      if (!tr) { cudaMalloc(&tr, 8192 * sizeof(long long)); }
+      cudaMemsetAsync(tr, 0, 8192 * sizeof(long long), st);
+      p.trace = tr;
+      g_umma16_trace = tr;
+    }
+#endif
+    const size_t smem = umma16::kuf_smem_plan(umma16::pad_k(v.D), TN, d->H * d->W * v.C, p.n_pt * TN, p.Mpad, nbuf).total;
+    const long long grid = std::max<long long>(G, std::min<long long>(p.n_units * G, num_sms()));
 #define CALL(PH_, PW_)                                                                                        \
   {                                                                                                           \
     void (*kernel)(const umma16::Params) = umma16::kuf_fwd_kernel<PH_, PW_, TN>;                              \
@@ -405,51 +436,61 @@ static int run_umma16_kuf_fwd(const cgp_kernel_desc* d, const Geo& g, int N, int
     }                                                                                                         \
     kernel<<<(unsigned)grid, umma16::kThreads, smem, st>>>(p);                                                \
     CGP_CUDA_CHECK(cudaGetLastError());                                                                       \
-    return CGP_OK;                                                                                            \
   }
-  CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+    if (d->ph == 5 && d->pw == 5) CALL(5, 5)
+    else if (d->ph == 3 && d->pw == 3) CALL(3, 3)
+    else if (d->ph == 2 && d->pw == 2) CALL(2, 2)
+    else { set_error("no specialised kernel for %dx%d patches", d->ph, d->pw); return CGP_ERR_UNSUPPORTED; }
 #undef CALL
-}
-
-// Kuf backward (umma16.cuh kuf_bwd_kernel): one (row tile, patch tile) pair and a range of images per CTA.
-static bool umma16_bwd_plan(const cgp_kernel_desc* d, const Geo& g, int mode) {
-  if (mode != 1 || d->dtype != CGP_F32 || d->out_mode == CGP_OUT_PER_CHANNEL) return false;
-  constexpr int TN = 192;
-  const int n_pt = (g.P + TN - 1) / TN;
-  return g.D + 2 <= 32 &&
-         umma16::bwd_smem_plan(umma16::pad_k(g.D), TN, d->H * d->W * d->C, n_pt * TN).total <= 227 * 1024;
-}
-
-static int run_umma16_kuf_bwd(const cgp_kernel_desc* d, const Geo& g, int N, int M, const void* X, const void* Z,
-                              const void* W, const void* var, const void* ls, const void* G, void* dZ, void* dW,
-                              void* dvar, void* dls, cudaStream_t st) {
-  constexpr int TN = 192;
-  umma16::BwdParams p;
-  memset(&p, 0, sizeof(p));
-  p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
-  p.ls = (const float*)ls; p.G = (const float*)G; p.dZ = (float*)dZ; p.dW = W ? (float*)dW : nullptr;
-  p.dvar = (float*)dvar; p.dls = (float*)dls;
-  p.N = N; p.M = M; p.H = d->H; p.Wd = d->W; p.C = d->C; p.Wout = g.Wout; p.Pc = g.Pc; p.P = g.P;
-  p.n_pt = (g.P + TN - 1) / TN;
-  p.n_zt = (M + umma16::TM - 1) / umma16::TM;
-  p.n_rp = (p.n_zt + 1) / 2;
-  const int pairs = p.n_pt * p.n_rp;
-  p.S = std::max(1, std::min(N, num_sms() / pairs));
-  p.Pn = (float)g.P;
-  if (N < 1 || M < 1) return CGP_OK;
-#ifdef CGP_UMMA_TRACE
-  {
-    static long long* tr = nullptr;
-    if (!tr) { cudaMalloc(&tr, 8192 * sizeof(long long)); }
-    cudaMemsetAsync(tr, 0, 8192 * sizeof(long long), st);
-    p.trace = tr;
-    g_umma16_trace = tr;
   }
-#endif
-  const size_t smem = umma16::bwd_smem_plan(umma16::pad_k(g.D), TN, d->H * d->W * d->C, p.n_pt * TN).total;
-  const unsigned grid = (unsigned)(pairs * p.S);
+  return CGP_OK;
+}
+
+// Kuf backward (umma16.cuh kuf_bwd_kernel): two row tiles, one patch tile and a range of images per CTA.
+static bool umma16_bwd_plan(const cgp_kernel_desc* d, const Geo& g, int mode) {
+  if (!u16_mode_ok(d, mode)) return false;
+  const U16View v = u16_view(d, g, mode, 0);
+  constexpr int TN = 192;
+  const int n_pt = (v.P + TN - 1) / TN;
+  return v.D + 2 <= 32 &&
+         umma16::bwd_smem_plan(umma16::pad_k(v.D), TN, d->H * d->W * v.C, n_pt * TN).total <= 227 * 1024;
+}
+
+static int run_umma16_kuf_bwd(const cgp_kernel_desc* d, const Geo& g, int mode, int N, int M, const void* X,
+                              const void* Z, const void* W, const void* var, const void* ls, const void* G, void* dZ,
+                              void* dW, void* dvar, void* dls, cudaStream_t st) {
+  constexpr int TN = 192;
+  if (N < 1 || M < 1) return CGP_OK;
   int dev = 0;
   CGP_CUDA_CHECK(cudaGetDevice(&dev));
+  {  // one launch: CTA b works on RBF group b % G
+    const int Gr = u16_groups(d, mode);
+    const U16View v = u16_view(d, g, mode, 0);
+    umma16::BwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.G = Gr;
+    p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
+    p.ls = (const float*)ls; p.G_up = (const float*)G; p.dZ = (float*)dZ; p.dW = W ? (float*)dW : nullptr;
+    p.dvar = (float*)dvar; p.dls = (float*)dls;
+    p.N = N; p.M = M; p.H = d->H; p.Wd = d->W; p.C = v.C; p.Wout = g.Wout; p.Pc = v.Pc; p.P = v.P;
+    p.Cx = v.Cx; p.choff = v.choff; p.zrow = v.zrow; p.zs = v.zs; p.zo = v.zo;
+    p.n_pt = (v.P + TN - 1) / TN;
+    p.n_zt = (M + umma16::TM - 1) / umma16::TM;
+    p.n_rp = (p.n_zt + 1) / 2;
+    const int pairs = p.n_pt * p.n_rp;
+    p.S = std::max(1, std::min(N, num_sms() / (pairs * Gr)));
+    p.Pn = (float)g.P;
+#ifdef CGP_UMMA_TRACE
+    {
+      static long long* tr = nullptr;
+      if (!tr) { cudaMalloc(&tr, 8192 * sizeof(long long)); }
+      cudaMemsetAsync(tr, 0, 8192 * sizeof(long long), st);
+      p.trace = tr;
+      g_umma16_trace = tr;
+    }
+#endif
+    const size_t smem = umma16::bwd_smem_plan(umma16::pad_k(v.D), TN, d->H * d->W * v.C, p.n_pt * TN).total;
+    const unsigned grid = (unsigned)(pairs * p.S * Gr);
 #define CALL(PH_, PW_)                                                                                        \
   {                                                                                                           \
     void (*kernel)(const umma16::BwdParams) = umma16::kuf_bwd_kernel<PH_, PW_, TN>;                           \
@@ -463,56 +504,73 @@ static int run_umma16_kuf_bwd(const cgp_kernel_desc* d, const Geo& g, int N, int
     }                                                                                                         \
     kernel<<<grid, umma16::kbThreads, smem, st>>>(p);                                                         \
     CGP_CUDA_CHECK(cudaGetLastError());                                                                       \
-    return CGP_OK;                                                                                            \
   }
-  CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+    if (d->ph == 5 && d->pw == 5) CALL(5, 5)
+    else if (d->ph == 3 && d->pw == 3) CALL(3, 3)
+    else if (d->ph == 2 && d->pw == 2) CALL(2, 2)
+    else { set_error("no specialised kernel for %dx%d patches", d->ph, d->pw); return CGP_ERR_UNSUPPORTED; }
 #undef CALL
+  }
+  return CGP_OK;
 }
 
 // Kdiag forward (umma16.cuh kdiag_fwd_kernel): one pairing domain per image, tiles on or above the diagonal only.
 static bool umma16_kdiag_plan(const cgp_kernel_desc* d, const Geo& g, int mode, int* nbuf_out) {
-  if (mode != 1 || d->dtype != CGP_F32 || d->out_mode == CGP_OUT_PER_CHANNEL) return false;
-  const int KD = umma16::pad_kd(g.D), nt = (g.P + 127) / 128;
+  if (!u16_mode_ok(d, mode)) return false;
+  const U16View v = u16_view(d, g, mode, 0);
+  const int KD = umma16::pad_kd(v.D), nt = (v.P + 127) / 128;
   for (int nbuf = 2; nbuf >= 1; --nbuf)
-    if (umma16::kd_smem_plan(KD, d->H * d->W * d->C, nt * 128, nbuf).total <= 227 * 1024) {
+    if (umma16::kd_smem_plan(KD, d->H * d->W * v.C, nt * 128, nbuf).total <= 227 * 1024) {
       if (nbuf_out) *nbuf_out = nbuf;
       return true;
     }
   return false;
 }
 
-static int run_umma16_kdiag(const cgp_kernel_desc* d, const Geo& g, int N, const void* X, const void* W,
+// `save` (or nullptr): mode 1: [N P] row sums | [N] v | [N] v2; mode 2 (G groups): [N P] variance-weighted row sums
+// summed over the groups | per group g: [N] v_g, [N] v2_g
+static int run_umma16_kdiag(const cgp_kernel_desc* d, const Geo& g, int mode, int N, const void* X, const void* W,
                             const void* var, const void* ls, void* out, void* save, cudaStream_t st) {
-  umma16::KdParams p;
-  memset(&p, 0, sizeof(p));
   int nbuf = 0;
-  if (!umma16_kdiag_plan(d, g, 1, &nbuf)) { set_error("umma16 kdiag: shared-memory plan does not fit"); return CGP_ERR_UNSUPPORTED; }
-  p.X = (const float*)X; p.Wt = (const float*)W; p.var = (const float*)var; p.ls = (const float*)ls;
-  p.out = (float*)out; p.save = (float*)save;
-  p.N = N; p.H = d->H; p.Wd = d->W; p.C = d->C; p.Wout = g.Wout; p.Pc = g.Pc; p.P = g.P;
-  p.nt = (g.P + 127) / 128;
-  p.NL = (g.P - 128 * (p.nt - 1)) <= 64 ? 64 : 128;
-  p.Rpad = p.nt * 128;
-  p.nbuf = nbuf;
-  p.cost_img = 0;
-  for (int i = 0; i < p.nt; ++i)
-    for (int j = i; j < p.nt; ++j) p.cost_img += (j == p.nt - 1 && p.NL == 64) ? 2 : 3;
-  p.Pn = (float)g.P;
+  if (!umma16_kdiag_plan(d, g, mode, &nbuf)) { set_error("umma16 kdiag: shared-memory plan does not fit"); return CGP_ERR_UNSUPPORTED; }
   if (N < 1) return CGP_OK;
-#ifdef CGP_UMMA_TRACE
-  {
-    static long long* tr = nullptr;
-    if (!tr) { cudaMalloc(&tr, 8192 * sizeof(long long)); }
-    cudaMemsetAsync(tr, 0, 8192 * sizeof(long long), st);
-    p.trace = tr;
-    g_umma16_trace = tr;
-  }
-#endif
-  const size_t smem = umma16::kd_smem_plan(umma16::pad_kd(g.D), d->H * d->W * d->C, p.Rpad, nbuf).total;
-  const long long units = (long long)N * p.nt * (p.nt + 1) / 2;
-  const long long grid = std::max<long long>(1, std::min<long long>(units, num_sms()));
   int dev = 0;
   CGP_CUDA_CHECK(cudaGetDevice(&dev));
+  {  // one launch: CTA b works on RBF group b % G
+    const int G = u16_groups(d, mode);
+    const U16View v = u16_view(d, g, mode, 0);
+    umma16::KdParams p;
+    memset(&p, 0, sizeof(p));
+    p.G = G;
+    p.X = (const float*)X; p.Wt = (const float*)W; p.var = (const float*)var; p.ls = (const float*)ls;
+    p.out = (float*)out; p.save = (float*)save;
+    if (save) {
+      p.save_v = (float*)save + (size_t)N * v.P;
+      p.save_v2 = p.save_v + N;
+      p.rscale = mode == 2;
+    }
+    p.N = N; p.H = d->H; p.Wd = d->W; p.C = v.C; p.Wout = g.Wout; p.Pc = v.Pc; p.P = v.P;
+    p.Cx = v.Cx; p.choff = v.choff;
+    p.nt = (v.P + 127) / 128;
+    p.NL = (v.P - 128 * (p.nt - 1)) <= 64 ? 64 : 128;
+    p.Rpad = p.nt * 128;
+    p.nbuf = nbuf;
+    p.cost_img = 0;
+    for (int i = 0; i < p.nt; ++i)
+      for (int j = i; j < p.nt; ++j) p.cost_img += (j == p.nt - 1 && p.NL == 64) ? 2 : 3;
+    p.Pn = (float)g.P;
+#ifdef CGP_UMMA_TRACE
+    {
+      static long long* tr = nullptr;
+      if (!tr) { cudaMalloc(&tr, 8192 * sizeof(long long)); }
+      cudaMemsetAsync(tr, 0, 8192 * sizeof(long long), st);
+      p.trace = tr;
+      g_umma16_trace = tr;
+    }
+#endif
+    const size_t smem = umma16::kd_smem_plan(umma16::pad_kd(v.D), d->H * d->W * v.C, p.Rpad, nbuf).total;
+    const long long units = (long long)N * p.nt * (p.nt + 1) / 2;
+    const long long grid = std::max<long long>(G, std::min<long long>(units * G, num_sms()));
 #define CALL(PH_, PW_)                                                                                        \
   {                                                                                                           \
     void (*kernel)(const umma16::KdParams) = umma16::kdiag_fwd_kernel<PH_, PW_>;                              \
@@ -526,10 +584,14 @@ static int run_umma16_kdiag(const cgp_kernel_desc* d, const Geo& g, int N, const
     }                                                                                                         \
     kernel<<<(unsigned)grid, umma16::kdThreads, smem, st>>>(p);                                               \
     CGP_CUDA_CHECK(cudaGetLastError());                                                                       \
-    return CGP_OK;                                                                                            \
   }
-  CGP_DISPATCH_PATCH(d->ph, d->pw, CALL)
+    if (d->ph == 5 && d->pw == 5) CALL(5, 5)
+    else if (d->ph == 3 && d->pw == 3) CALL(3, 3)
+    else if (d->ph == 2 && d->pw == 2) CALL(2, 2)
+    else { set_error("no specialised kernel for %dx%d patches", d->ph, d->pw); return CGP_ERR_UNSUPPORTED; }
 #undef CALL
+  }
+  return CGP_OK;
 }
 
 // float32 Kdiag forward family: 3 umma16 | 2 umma32 | 1 hmma32 | 0 scalar (what the option asks for, lowered to
@@ -611,9 +673,9 @@ static int run_kuf_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int N,
   if constexpr (std::is_same<T, float>::value) {
     int fam = opt(BWD ? g_opt.kuf_bwd_f32 : g_opt.kuf_fwd_f32, 3);  // 3 umma16 | 2 umma32 | 1 hmma32 | 0 scalar
     if (!BWD && fam == 3 && umma16_kuf_plan(d, g, mode, M, nullptr))
-      return run_umma16_kuf_fwd(d, g, N, M, X, Z, W, var, ls, out, st);
+      return run_umma16_kuf_fwd(d, g, mode, N, M, X, Z, W, var, ls, out, st);
     if (BWD && fam == 3 && umma16_bwd_plan(d, g, mode))
-      return run_umma16_kuf_bwd(d, g, N, M, X, Z, W, var, ls, G, dZ, dW, dvar, dls, st);
+      return run_umma16_kuf_bwd(d, g, mode, N, M, X, Z, W, var, ls, G, dZ, dW, dvar, dls, st);
     if (fam == 3) fam = 2;
     if (fam == 2 && umma_ok(d, g, mode, M) &&
         umma::dz_smem_plan(umma::pad_k(g.D), d->H * d->W, g.P).total <= 227 * 1024) {
@@ -723,7 +785,7 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
   }
   if constexpr (std::is_same<T, float>::value) {
     if (!BWD && kdiag_fwd_f32_family(d, g, mode) == 3)
-      return run_umma16_kdiag(d, g, N, X, W, var, ls, out, nullptr, st);
+      return run_umma16_kdiag(d, g, mode, N, X, W, var, ls, out, nullptr, st);
     if (use_tc32 >= 2 && umma_ok(d, g, mode, 0))
       return run_umma_rowsum(BWD ? 2 : 1, d, g, N, 0, X, nullptr, W, var, ls, G, out, dW, dvar, dls, st);
   }
@@ -766,19 +828,24 @@ static int run_kdiag_fast(const cgp_kernel_desc* d, const Geo& g, int mode, int 
 // Supported by the default family of each dtype (float32: tcgen05 row-sum kernel, float64: FP64 warp-MMA kernel)
 // when the image is one pairing domain with one RBF; otherwise the caller keeps the two-pass pair.
 static bool kdiag_saved_ok(const cgp_kernel_desc* d, const Geo& g, int mode) {
-  if (mode != 1 || d->out_mode == CGP_OUT_PER_CHANNEL) return false;
-  if (d->dtype == CGP_F32)
-    return kdiag_fwd_f32_family(d, g, mode) >= 2 && opt(g_opt.kdiag_bwd_f32, 3) >= 2;
-  return opt(g_opt.kdiag_fwd, 1) != 0 && opt(g_opt.kdiag_bwd, 1) != 0;
+  if (d->out_mode == CGP_OUT_PER_CHANNEL) return false;
+  if (d->dtype == CGP_F32) {
+    const int fam = kdiag_fwd_f32_family(d, g, mode);
+    // several RBF groups (mode 2) only through the umma16 family, whose launches accumulate into one saved buffer
+    return (mode == 1 ? fam >= 2 : (mode == 2 && fam == 3)) && opt(g_opt.kdiag_bwd_f32, 3) >= 2;
+  }
+  return mode == 1 && opt(g_opt.kdiag_fwd, 1) != 0 && opt(g_opt.kdiag_bwd, 1) != 0;
 }
+// saved elements per image beyond the P row sums: (v, v2) per RBF group
+static int kdiag_saved_groups(const cgp_kernel_desc* d, int mode) { return mode == 2 ? d->C : 1; }
 
 template <typename T>
 static int run_kdiag_saved_fwd(const cgp_kernel_desc* d, const Geo& g, int mode, int N, const void* X, const void* W,
                                const void* var, const void* ls, void* out, void* save, cudaStream_t st) {
   CGP_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(T) * (size_t)N, st));
-  CGP_CUDA_CHECK(cudaMemsetAsync(save, 0, sizeof(T) * (size_t)N * (g.P + 2), st));
+  CGP_CUDA_CHECK(cudaMemsetAsync(save, 0, sizeof(T) * (size_t)N * (g.P + 2 * kdiag_saved_groups(d, mode)), st));
   if constexpr (std::is_same<T, float>::value) {
-    if (kdiag_fwd_f32_family(d, g, mode) == 3) return run_umma16_kdiag(d, g, N, X, W, var, ls, out, save, st);
+    if (kdiag_fwd_f32_family(d, g, mode) == 3) return run_umma16_kdiag(d, g, mode, N, X, W, var, ls, out, save, st);
     return run_umma_rowsum(4, d, g, N, 0, X, nullptr, W, var, ls, nullptr, out, nullptr, nullptr, nullptr, st, save);
   } else {
     FastParams<T> p;
@@ -804,39 +871,42 @@ static int run_kdiag_saved_fwd(const cgp_kernel_desc* d, const Geo& g, int mode,
 }
 
 // grid (ceil(P / 256), image chunks): thread q sums g[n] r[n, q] over its chunk of images (coalesced in q)
+// G > 1 (several RBF groups): the saved row sums already carry the groups' variances, (v, v2) are stored per group
 template <typename T>
-__global__ void kdiag_bwd_saved_kernel(int N, int P, const T* __restrict__ g, const T* __restrict__ save,
+__global__ void kdiag_bwd_saved_kernel(int N, int P, int G, const T* __restrict__ g, const T* __restrict__ save,
                                        const T* __restrict__ var, const T* __restrict__ ls, T* dW, T* dvar, T* dls,
                                        T P2, T arg_scale) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = (N + gridDim.y - 1) / gridDim.y, n0 = blockIdx.y * per, n1 = min(N, n0 + per);
-  const T sig2 = var[0], lsv = ls[0];
   if (q < P && dW) {
     T acc = T(0);
     for (int n = n0; n < n1; ++n) acc = fma_t(g[n], save[(size_t)n * P + q], acc);
-    atomicAdd(dW + q, T(2) * sig2 / P2 * acc);
+    atomicAdd(dW + q, T(2) * (G > 1 ? T(1) : var[0]) / P2 * acc);
   }
-  if (blockIdx.x == 0 && threadIdx.x < 32) {  // the two scalar gradients: one warp per image chunk
-    T a = T(0), b = T(0);
-    for (int n = n0 + (int)threadIdx.x; n < n1; n += 32) {
-      a = fma_t(g[n], save[(size_t)N * P + n], a);
-      b = fma_t(g[n], save[(size_t)N * P + N + n], b);
-    }
-    a = warp_sum(a);
-    b = warp_sum(b);
-    if (threadIdx.x == 0) {
-      if (dvar) atomicAdd(dvar, a / P2);
-      if (dls) atomicAdd(dls, T(-2) * sig2 / lsv * b / P2 / arg_scale);
+  if (blockIdx.x == 0 && threadIdx.x < 32) {  // the scalar gradients: one warp per image chunk
+    for (int gi = 0; gi < G; ++gi) {
+      const T* sv = save + (size_t)N * P + (size_t)(2 * gi) * N;
+      T a = T(0), b = T(0);
+      for (int n = n0 + (int)threadIdx.x; n < n1; n += 32) {
+        a = fma_t(g[n], sv[n], a);
+        b = fma_t(g[n], sv[N + n], b);
+      }
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (threadIdx.x == 0) {
+        if (dvar) atomicAdd(dvar + gi, a / P2);
+        if (dls) atomicAdd(dls + gi, T(-2) * var[gi] / ls[gi] * b / P2 / arg_scale);
+      }
     }
   }
 }
 
 template <typename T>
-static int run_kdiag_saved_bwd(const Geo& g, int N, const void* gK, const void* save, const void* var, const void* ls,
-                               void* dW, void* dvar, void* dls, cudaStream_t st) {
+static int run_kdiag_saved_bwd(const Geo& g, int G, int N, const void* gK, const void* save, const void* var,
+                               const void* ls, void* dW, void* dvar, void* dls, cudaStream_t st) {
   const int tpb = 256;
   dim3 grid((g.P + tpb - 1) / tpb, std::max(1, std::min(N, 32)));
-  kdiag_bwd_saved_kernel<T><<<grid, tpb, 0, st>>>(N, g.P, (const T*)gK, (const T*)save, (const T*)var, (const T*)ls,
+  kdiag_bwd_saved_kernel<T><<<grid, tpb, 0, st>>>(N, g.P, G, (const T*)gK, (const T*)save, (const T*)var, (const T*)ls,
                                                   (T*)dW, (T*)dvar, (T*)dls, (T)((double)g.P * (double)g.P),
                                                   (T)Math<T>::kArgScale);
   CGP_CUDA_CHECK(cudaGetLastError());
@@ -1145,7 +1215,7 @@ size_t cgp_kdiag_saved_elems(const cgp_kernel_desc* d, int32_t N) {
   if (geometry(d, &g) != CGP_OK || N < 1) return 0;
   const int mode = fast_mode(d, g);
   if (!mode || !kdiag_saved_ok(d, g, mode)) return 0;
-  return (size_t)N * (g.P + 2);
+  return (size_t)N * (g.P + 2 * kdiag_saved_groups(d, mode));
 }
 
 int cgp_kdiag_fwd_saved(const cgp_kernel_desc* d, int32_t N, const void* X, const void* W, const void* variance,
@@ -1160,7 +1230,7 @@ int cgp_kdiag_fwd_saved(const cgp_kernel_desc* d, int32_t N, const void* X, cons
     set_error("kdiag_fwd_saved: configuration not covered (cgp_kdiag_saved_elems returns 0): use cgp_kdiag_fwd/bwd");
     return CGP_ERR_UNSUPPORTED;
   }
-  if (saved_elems < (size_t)N * (g.P + 2)) { set_error("kdiag_fwd_saved: saved buffer too small"); return CGP_ERR_WORKSPACE; }
+  if (saved_elems < (size_t)N * (g.P + 2 * kdiag_saved_groups(d, mode))) { set_error("kdiag_fwd_saved: saved buffer too small"); return CGP_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   if (d->dtype == CGP_F64)
     return run_kdiag_saved_fwd<double>(d, g, mode, N, X, W, variance, lengthscales, Kdiag, saved, st);
@@ -1180,11 +1250,12 @@ int cgp_kdiag_bwd_saved(const cgp_kernel_desc* d, int32_t N, const void* varianc
     set_error("kdiag_bwd_saved: configuration not covered (cgp_kdiag_saved_elems returns 0)");
     return CGP_ERR_UNSUPPORTED;
   }
-  if (saved_elems < (size_t)N * (g.P + 2)) { set_error("kdiag_bwd_saved: saved buffer too small"); return CGP_ERR_WORKSPACE; }
+  const int G = kdiag_saved_groups(d, mode);
+  if (saved_elems < (size_t)N * (g.P + 2 * G)) { set_error("kdiag_bwd_saved: saved buffer too small"); return CGP_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   if (d->dtype == CGP_F64)
-    return run_kdiag_saved_bwd<double>(g, N, gK, saved, variance, lengthscales, dW, dvariance, dlengthscales, st);
-  return run_kdiag_saved_bwd<float>(g, N, gK, saved, variance, lengthscales, dW, dvariance, dlengthscales, st);
+    return run_kdiag_saved_bwd<double>(g, G, N, gK, saved, variance, lengthscales, dW, dvariance, dlengthscales, st);
+  return run_kdiag_saved_bwd<float>(g, G, N, gK, saved, variance, lengthscales, dW, dvariance, dlengthscales, st);
 }
 
 int cgp_kuu_fwd(const cgp_kernel_desc* d, int32_t M, const void* Z, const void* variance,

@@ -59,6 +59,10 @@ struct Params {
   float* out;   // Kuf (M, N) / Kdiag (N)
   float* save;  // Kdiag: [N * P] row sums, [N] sum_q w_q r, [N] sum w w k S (or nullptr)
   int N, M, H, Wd, C, Hout, Wout, Pc, P, D;
+  int Cx, choff;      // channels of the image in memory and the staged channel when C == 1 < Cx (else Cx == C, choff = 0)
+  int zrow, zs, zo;   // element d of inducing row m is Z[m * zrow + d * zs + zo] (planar: D, 1, 0; colour group g: C D, C, g)
+  int G;              // RBF groups handled by this launch: CTA b works on group b % G (var[g], ls[g], channel choff + g,
+                      // Z offset zo + g) and shares that group's units with the other CTAs of the group
   int n_pt;    // patch column tiles per image
   int n_zt;    // inducing row tiles
   int Mpad;    // n_zt * TM
@@ -164,14 +168,19 @@ __device__ __forceinline__ void put_row(unsigned char* buf, int R, int r, const 
 __host__ __device__ inline int al16(int bytes) { return (bytes + 15) / 16 * 16; }
 
 // One image -> shared memory with cp.async, completion on an mbarrier (count = nthreads): every calling thread copies
-// its pieces and arrives when they have landed.
+// its pieces and arrives when they have landed.  cx > c: only channel `choff` of a channel-minor image with cx channels
+// is staged (one RBF group of the colour-patch additive kernel sees one colour plane: cifar.py:33-41).
 __device__ __forceinline__ void fetch_image_async(float* dst, const float* src, int n_floats, int t, int nthreads,
-                                                  uint64_t* bar) {
-  const bool x16 = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (n_floats & 3) == 0;
-  if (x16)
-    for (int i = t; i < n_floats / 4; i += nthreads) umma::cp_async16(dst + 4 * i, src + 4 * i);
-  else
-    for (int i = t; i < n_floats; i += nthreads) umma::cp_async4(dst + i, src + i);
+                                                  uint64_t* bar, int gather_stride = 1, int gather_off = 0) {
+  if (gather_stride == 1) {
+    const bool x16 = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (n_floats & 3) == 0;
+    if (x16)
+      for (int i = t; i < n_floats / 4; i += nthreads) umma::cp_async16(dst + 4 * i, src + 4 * i);
+    else
+      for (int i = t; i < n_floats; i += nthreads) umma::cp_async4(dst + i, src + i);
+  } else {
+    for (int i = t; i < n_floats; i += nthreads) umma::cp_async4(dst + i, src + (size_t)i * gather_stride + gather_off);
+  }
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
@@ -239,8 +248,10 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long lo = p.n_units * blockIdx.x / gridDim.x;
-  const long long hi = p.n_units * (blockIdx.x + 1) / gridDim.x;
+  const int grp = blockIdx.x % p.G, cta = blockIdx.x / p.G, ncta = ((int)gridDim.x - grp + p.G - 1) / p.G;
+  const int choff = p.choff + grp, zo = p.zo + grp;
+  const long long lo = p.n_units * cta / ncta;
+  const long long hi = p.n_units * (cta + 1) / ncta;
   const int nun = (int)(hi - lo);
   const int per_img = p.n_pt * p.n_zt;
   const int n0 = (int)(lo / per_img);
@@ -254,13 +265,14 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
   }
   __syncthreads();
   if (warp < kProd / 32 && nun > 0)
-    fetch_image_async(raw0, p.X + (size_t)n0 * (p.H * p.Wd * p.C), p.H * p.Wd * p.C, tid, kProd, &img_bar[0]);
+    fetch_image_async(raw0, p.X + (size_t)n0 * (p.H * p.Wd * p.Cx), p.H * p.Wd * p.C, tid, kProd, &img_bar[0],
+                      p.Cx / p.C, choff);
   {  // warm the L2 for the inducing patches too
     const char* zb = reinterpret_cast<const char*>(p.Z);
-    const int zbytes = p.M * D * 4;
+    const int zbytes = p.M * p.zrow * 4;
     for (int o = tid * 128; o < zbytes; o += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(zb + o));
   }
-  const float lsv = p.ls[0], sig2 = p.var[0];
+  const float lsv = p.ls[grp], sig2 = p.var[grp];
 
   for (int i = tid; i < Ppad; i += kThreads) {
     const int q = min(i, p.P - 1);  // rows past the last patch repeat it (finite exponents); their weight is zero
@@ -301,7 +313,8 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
     // ============================== producers: images -> packed fp16 pairs -> patch tiles
     const int pt = tid;
     auto fetch_image = [&](int n, int k) {
-      fetch_image_async(raw0 + (k % 3) * raw_stride, p.X + (size_t)n * HWC, HWC, pt, kProd, &img_bar[k % 3]);
+      fetch_image_async(raw0 + (k % 3) * raw_stride, p.X + (size_t)n * HWC * (p.Cx / p.C), HWC, pt, kProd,
+                        &img_bar[k % 3], p.Cx / p.C, choff);
     };
     int n = n0, j = j0, ki = -1, cur = -1;
     int u = 0, tile = 0;
@@ -413,11 +426,11 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
 #pragma unroll
         for (int d = 0; d < KP; ++d) v[d] = 0u;
         if (r < p.M) {
-          const float* z = p.Z + (size_t)r * D;
+          const float* z = p.Z + (size_t)r * p.zrow + zo;
           float ss = 0.f;
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            const float x = z[d];
+            const float x = z[d * p.zs];
             ss = fmaf(x, x, ss);
             v[d] = split_f16(x * sc);
           }
@@ -547,6 +560,10 @@ struct KdParams {
   float* out;   // Kdiag (N), zero-initialised
   float* save;  // [N * P] row sums, [N] v, [N] v2 (zero-initialised) or nullptr
   int N, H, Wd, C, Wout, Pc, P;
+  int Cx, choff, G;  // see Params (group g also uses save_v + 2 g N, save_v2 + 2 g N)
+  float* save_v;  // [N] sum_q w_q r and [N] sum w w k * exponent of this launch's RBF group
+  float* save_v2;
+  int rscale;     // 1: the saved row sums carry the group's variance (several groups accumulate into them)
   int nt;    // row / column tiles of 128
   int NL;    // columns of the last column tile (64 or 128)
   int Rpad;  // 128 nt rows staged per image
@@ -620,8 +637,10 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) CGP_T16(0);
   // work split by cost: CTA b owns the units whose first cost unit lies in [total b / B, total (b + 1) / B)
+  const int grp = blockIdx.x % p.G, cta = blockIdx.x / p.G, ncta = ((int)gridDim.x - grp + p.G - 1) / p.G;
+  const int choff = p.choff + grp;
   const long long total = (long long)p.N * p.cost_img;
-  const long long clo = total * blockIdx.x / gridDim.x, chi = total * (blockIdx.x + 1) / gridDim.x;
+  const long long clo = total * cta / ncta, chi = total * (cta + 1) / ncta;
   const int nt = p.nt;
   auto unit_cost = [&](int j) { return j == nt - 1 && p.NL == 64 ? 2 : 3; };  // measured: 2 250 vs 1 500 cycles
   // first unit at or after cost `c` of the image-local scan
@@ -658,8 +677,8 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
   }
   __syncthreads();
   if (warp < kdProd / 32 && nun > 0)
-    fetch_image_async(raw0, p.X + (size_t)n_first * HWC, HWC, tid, kdProd, &img_bar[0]);
-  const float lsv = p.ls[0], sig2 = p.var[0];
+    fetch_image_async(raw0, p.X + (size_t)n_first * HWC * (p.Cx / p.C), HWC, tid, kdProd, &img_bar[0], p.Cx / p.C, choff);
+  const float lsv = p.ls[grp], sig2 = p.var[grp];
   for (int i = tid; i < Rpad; i += kdThreads) {
     const int q = min(i, p.P - 1);
     const int c = q / p.Pc, pos = q % p.Pc;
@@ -700,7 +719,8 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
     // ============================== producers: one image -> every patch row, once
     const int pt = tid;
     auto fetch_image = [&](int n, int k) {
-      fetch_image_async(raw0 + (k % 3) * raw_stride, p.X + (size_t)n * HWC, HWC, pt, kdProd, &img_bar[k % 3]);
+      fetch_image_async(raw0 + (k % 3) * raw_stride, p.X + (size_t)n * HWC * (p.Cx / p.C), HWC, pt, kdProd,
+                        &img_bar[k % 3], p.Cx / p.C, choff);
     };
     // number of images: walk the units
     int n_imgs = 0;
@@ -814,7 +834,7 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
         if (q < p.P) {
           v1 = fmaf(w[q], r, v1);
           v2 = fmaf(w[q], r2, v2);
-          if (p.save) atomicAdd(p.save + (size_t)n * p.P + q, r);  // an image can be shared by two CTAs
+          if (p.save) atomicAdd(p.save + (size_t)n * p.P + q, p.rscale ? sig2 * r : r);  // (an image can be shared by two CTAs)
         }
       }
       const float v = epi_sum(v1);
@@ -822,8 +842,8 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
       if (et == 0) {
         atomicAdd(p.out + n, v * s_kd);
         if (p.save) {
-          atomicAdd(p.save + (size_t)p.N * p.P + n, v);
-          atomicAdd(p.save + (size_t)p.N * p.P + p.N + n, vv);
+          atomicAdd(p.save_v + (size_t)(2 * grp) * p.N + n, v);
+          atomicAdd(p.save_v2 + (size_t)(2 * grp) * p.N + n, vv);
         }
       }
     };
@@ -965,12 +985,13 @@ struct BwdParams {
   const float* Wt;
   const float* var;
   const float* ls;
-  const float* G;  // dL/dKuf (M, N)
+  const float* G_up;  // dL/dKuf (M, N)
   float* dZ;
   float* dW;
   float* dvar;
   float* dls;
   int N, M, H, Wd, C, Wout, Pc, P;
+  int Cx, choff, zrow, zs, zo, G;  // see Params (group g accumulates dvar[g], dls[g])
   int n_pt, n_zt, n_rp, S;  // patch tiles, row tiles, row-tile pairs, image shares per (row-tile pair, patch tile)
   float Pn;
   long long* trace;
@@ -1062,7 +1083,9 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = blockIdx.x / p.S, share = blockIdx.x % p.S;
+  const int kg = blockIdx.x % p.G, rest = blockIdx.x / p.G;  // RBF group of this CTA
+  const int choff = p.choff + kg, zo = p.zo + kg;
+  const int grp = rest / p.S, share = rest % p.S;
   const int rp = grp / p.n_pt, jt = grp % p.n_pt;  // row-tile pair, patch tile
   const int nrt = min(2, p.n_zt - 2 * rp);         // row tiles of this CTA
   const int n_lo = (int)((long long)p.N * share / p.S), n_hi = (int)((long long)p.N * (share + 1) / p.S);
@@ -1076,8 +1099,9 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
   }
   __syncthreads();
   if (warp >= kbProdWarp0 && warp < kbIssuerWarp && nimg > 0)
-    fetch_image_async(raw0, p.X + (size_t)n_lo * HWC, HWC, tid - kbProdWarp0 * 32, kbProd, &img_bar[0]);
-  const float lsv = p.ls[0], sig2 = p.var[0];
+    fetch_image_async(raw0, p.X + (size_t)n_lo * HWC * (p.Cx / p.C), HWC, tid - kbProdWarp0 * 32, kbProd, &img_bar[0],
+                      p.Cx / p.C, choff);
+  const float lsv = p.ls[kg], sig2 = p.var[kg];
   for (int i = tid; i < Ppad; i += kbThreads) {
     const int q = min(i, p.P - 1);
     const int c = q / p.Pc, pos = q % p.Pc;
@@ -1128,7 +1152,8 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
     // ============================== producers (one pass per image)
     const int pt = tid - kbProdWarp0 * 32;
     auto fetch_image = [&](int n, int k) {
-      fetch_image_async(raw0 + (k % 3) * raw_stride, p.X + (size_t)n * HWC, HWC, pt, kbProd, &img_bar[k % 3]);
+      fetch_image_async(raw0 + (k % 3) * raw_stride, p.X + (size_t)n * HWC * (p.Cx / p.C), HWC, pt, kbProd,
+                        &img_bar[k % 3], p.Cx / p.C, choff);
     };
     uint32_t oct_mask = 0;
     for (int o = 0; o < TN / 8; ++o) oct_mask |= oct_ok[o] ? (1u << o) : 0u;
@@ -1321,11 +1346,11 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
 #pragma unroll
       for (int d = 0; d < KP; ++d) v[d] = 0u;
       if (third < nrt && mz < p.M) {
-        const float* z = p.Z + (size_t)mz * D;
+        const float* z = p.Z + (size_t)mz * p.zrow + zo;
         float ss = 0.f;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          const float x = z[d];
+          const float x = z[d * p.zs];
           ss = fmaf(x, x, ss);
           v[d] = split_f16(x * sc);
         }
@@ -1349,8 +1374,8 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
     {
       float gm = 0.f, wm = 0.f;
       for (int n = n_lo + third; n < n_hi; n += 3) {
-        if (va) gm = fmaxf(gm, fabsf(p.G[(size_t)ma * p.N + n]));
-        if (vb) gm = fmaxf(gm, fabsf(p.G[(size_t)mb * p.N + n]));
+        if (va) gm = fmaxf(gm, fabsf(p.G_up[(size_t)ma * p.N + n]));
+        if (vb) gm = fmaxf(gm, fabsf(p.G_up[(size_t)mb * p.N + n]));
       }
       for (int i = et; i < TN; i += kbEpi) wm = fmaxf(wm, fabsf(w[c0p + i]));
 #pragma unroll
@@ -1383,14 +1408,14 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
     float dwacc[CW];  // these rows' sum over the CTA's images of c0, for each of this warp's 64 columns
 #pragma unroll
     for (int t = 0; t < CW; ++t) dwacc[t] = 0.f;
-    float ga = (nun > 0 && va) ? p.G[(size_t)ma * p.N + n_lo] : 0.f;
-    float gb = (nun > 0 && vb) ? p.G[(size_t)mb * p.N + n_lo] : 0.f;
+    float ga = (nun > 0 && va) ? p.G_up[(size_t)ma * p.N + n_lo] : 0.f;
+    float gb = (nun > 0 && vb) ? p.G_up[(size_t)mb * p.N + n_lo] : 0.f;
     for (int u = 0; u < nun; ++u) {
       const int k = nrt == 2 ? u >> 1 : u, rt = u - k * nrt;
       const float Gm = (rt == 0 ? ga : gb) * gs;
       if (rt == nrt - 1 && k + 1 < nimg) {  // next image's upstream gradients, a unit ahead
-        if (va) ga = p.G[(size_t)ma * p.N + n_lo + k + 1];
-        if (vb) gb = p.G[(size_t)mb * p.N + n_lo + k + 1];
+        if (va) ga = p.G_up[(size_t)ma * p.N + n_lo + k + 1];
+        if (vb) gb = p.G_up[(size_t)mb * p.N + n_lo + k + 1];
       }
       mbar_wait(&g1_done[u & 1], (u >> 1) & 1);
       if (et == 0) CGP_TU(6, u);
@@ -1459,7 +1484,7 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
       tmem_wait_ld(d1);
       tmem_wait_ld(d2);
       if (mz < p.M) {
-        const float* zr = p.Z + (size_t)mz * D;
+        const float* zr = p.Z + (size_t)mz * p.zrow + zo;
         s0row = (__uint_as_float(d1[D]) + __uint_as_float(d2[D])) * inv_cscale;
         const float qv = (__uint_as_float(d1[D + 1]) + __uint_as_float(d2[D + 1])) * inv_cscale;
         const float scz = sig2 / (lsv * lsv), unsc = inv_cscale / sc;  // the data rows carried sqrt(2 c2) x
@@ -1467,9 +1492,9 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           const float dz = (__uint_as_float(d1[d]) + __uint_as_float(d2[d])) * unsc;
-          const float zd = zr[d];
+          const float zd = zr[d * p.zs];
           zdot = fmaf(zd, dz, zdot);
-          if (p.dZ) atomicAdd(p.dZ + (size_t)mz * D + d, scz * (dz - zd * s0row));
+          if (p.dZ) atomicAdd(p.dZ + (size_t)mz * p.zrow + d * p.zs + zo, scz * (dz - zd * s0row));
         }
         slrow = 2.f * c2 * zdot - znorm * s0row - c2 * qv;  // sum_p cf S, S in log2 units
       }
@@ -1488,8 +1513,8 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
           a0 += red[k2];
           a2 += red[16 + k2];
         }
-        if (p.dvar) atomicAdd(p.dvar, a0);
-        if (p.dls) atomicAdd(p.dls, -2.f * sig2 / lsv * a2 / 1.4426950408889634f);
+        if (p.dvar) atomicAdd(p.dvar + kg, a0);
+        if (p.dls) atomicAdd(p.dls + kg, -2.f * sig2 / lsv * a2 / 1.4426950408889634f);
       }
     }
   }

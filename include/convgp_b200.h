@@ -103,6 +103,8 @@ int cgp_kdiag_bwd(const cgp_kernel_desc* d, int32_t N, const void* X, const void
  * (the reference gets this for free from TF autodiff, which keeps the P x P Gram of convkernels.py:173-181
  * alive between the passes; here only N * (P + 2) elements are kept: per image the row sums
  * r[n, q] = sum_q' w_q' k(x_nq, x_nq'), v[n] = sum_q w_q r[n, q] and v2[n] = sum w w k * arg).
+ * With several RBF groups (float32 colour-patch additive kernel) the row sums carry the groups' variances and (v, v2)
+ * are kept per group: N * (P + 2 n_groups) elements.
  * cgp_kdiag_saved_elems returns the element count of `saved` (caller-owned, dtype of the descriptor), or 0
  * when the configuration is not covered -- then use cgp_kdiag_fwd / cgp_kdiag_bwd. */
 size_t cgp_kdiag_saved_elems(const cgp_kernel_desc* d, int32_t N);

@@ -174,9 +174,15 @@ def test_options_api_and_family_query():
     for which in (0, 1, 2):  # Kuf forward / backward, Kdiag forward: the two-fp16-term tcgen05 family by default
         assert L.cgp_kernel_family(f32.ref(), 200, 750, which) == b"umma16"
     # planar colour images (Conv with colour_channels = 3: one pairing domain) take the same family when the
-    # shared-memory plan fits; per-channel outputs and the colour-patch additive kernel do not
+    # shared-memory plan fits; per-channel outputs do not
     rgb = _lib.Spec(torch.float32, 16, 16, 3, 5, 5, _lib.LAYOUT_PLANAR, _lib.OUT_SUM, 1, False, False)
     assert all(L.cgp_kernel_family(rgb.ref(), 30, 100, w) == b"umma16" for w in (0, 1, 2))
+    # config 5: colour patches with one RBF per channel (cifar.py:33-41) = one launch whose CTAs split over the groups
+    mask = np.array([[(dd % 3) == gg for dd in range(75)] for gg in range(3)], dtype=np.uint8)
+    cifar = _lib.Spec(torch.float32, 32, 32, 3, 5, 5, _lib.LAYOUT_COLOUR_PATCH, _lib.OUT_SUM, 3, False, True, mask)
+    assert [L.cgp_kernel_family(cifar.ref(), 30, 1000, w) for w in (0, 1, 2, 3)] == \
+        [b"umma16", b"umma16", b"umma16", b"saved-row-sums"]
+    assert L.cgp_kdiag_saved_elems(cifar.ref(), 30) == 30 * (784 + 2 * 3)
     multi = _lib.Spec(torch.float32, 16, 16, 3, 5, 5, _lib.LAYOUT_PLANAR, _lib.OUT_PER_CHANNEL, 1, False, False)
     assert L.cgp_kernel_family(multi.ref(), 30, 100, 0) != b"umma16"
     _lib.set_option("kuf_fwd_f32", 2)
