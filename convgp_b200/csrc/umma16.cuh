@@ -1,22 +1,29 @@
-// float32 kernels on the 5th-generation tensor cores, second generation: both operands of the patch contraction
-// live in shared memory as TWO fp16 TERMS (x = x1 + x2, 22 significant bits) and the MMA is tcgen05.mma
-// kind::f16 in its shared-memory x shared-memory form,
-//     a . b ~= a1.b1 + a1.b2 + a2.b1            (3 MMAs of K = 16; the 3xTF32 split of umma32.cuh needs 3 of K = 8)
+// float32 kernels on the 5th-generation tensor cores, second generation (the float32 default): both
+// operands of the patch contraction live in shared memory as TWO fp16 TERMS (x = x1 + x2, 22 significant bits) and the
+// MMA is tcgen05.mma kind::f16 in its shared-memory x shared-memory form,
+//     a . b ~= a2.b1 + a1.b2 + a1.b1            (3 MMAs of K = 16; the 3xTF32 split of umma32.cuh needs 3 of K = 8)
 // so a 128 x 192 tile of exponents costs 6 MMAs (~580 tensor-pipe cycles) against the 1536 cycles its 24 576
 // exps occupy the MUFU pipe -- and, unlike umma32.cuh, NO operand is restaged per tile:
-//   * Kuf forward   the scaled inducing patches (all row tiles) are written to shared memory once per CTA; the
-//                   patches of an image are staged one 192-patch tile at a time, straight from the image held in
-//                   shared memory as packed fp16 pairs, into a three-deep ring that six row tiles consume;
-//   * Kdiag forward the patches of an image are staged once and serve as BOTH operands; only the tiles on or
-//                   above the diagonal are evaluated, mirrored tiles give row sums and column sums.
+//   * kuf_fwd_kernel    the scaled inducing patches (all row tiles) are written to shared memory once per CTA; the
+//                       patches of an image are staged one 192-patch tile at a time, straight from the image held in
+//                       shared memory as packed fp16 pairs, into a three-deep ring that six row tiles consume;
+//   * kdiag_fwd_kernel  the patches of an image are staged once and serve as BOTH operands; only the tiles on or
+//                       above the diagonal are evaluated, mirrored tiles give row sums and column sums;
+//   * kuf_bwd_kernel    dZ, dW, dvariance, dlengthscale in one kernel: S = Z X^T as above, the coefficients
+//                       G / P * ex2(S) * w go back through TMEM as two fp16 terms into a second GEMM against
+//                       [x | 1 | |x|^2], dW's column sums stay in registers for the CTA's life.
 // The producer chain gather -> split -> tcgen05.st -> fence that bounded the umma32 kernels
-// is gone; what is left per tile is the issuer's six MMAs and the epilogue (tcgen05.ld -> ex2 -> FMA), twelve
+// is gone; what is left per tile is the issuer's MMAs and the epilogue (tcgen05.ld -> ex2 -> FMA), twelve
 // warps wide.  Four spare inner slots carry the squared norms as three fp16 terms each, so the accumulator IS the
 // RBF exponent in log2 units (convkernels.py:222-224: |x|^2 - 2 x.z + |z|^2):
 //     slot   D       D+1        D+2    D+3
 //     A      e1|e2   1          e3     1            e = -c2 |a|^2 = e1 + e2 + e3
 //     B      1       f1|f2      1      f3           f = -c2 |b|^2,   c2 = log2(e) / (2 l^2)
 // and the data slots hold sqrt(2 c2) * value on both sides.
+//
+// Coverage: summed output; planar layout with one RBF over the patch (any channel count: all C P' patches are one
+// pairing domain) and the colour-patch layout with one RBF per channel (cifar.py:33-41), which is the sum over the
+// channels of the single-plane problem: CTA b of a launch works on RBF group b mod G (Params::G).
 //
 // Range: fp16 overflows above 65504, so this family needs c2 |patch|^2 < 6e4, i.e. |patch| / l < 288 (pixel data
 // in [0, 1] with 5x5 patches: l > 0.018).  Outside that range the result is NaN (inf - inf), never a silently
