@@ -506,8 +506,9 @@ def measure_e2e(ctx, cfg, dtype_name, hp, inp, tens, steps):
     def e2e_body(b):
         for t in free:
             t.grad = None
-        # the package's own evaluation of one SVGP prediction's kernel terms (kernels.concurrent: parallel streams)
-        kuf, kd, kuu = bk.concurrent(lambda: kern.Kzx(Zp, X_dev[b]), lambda: kern.Kdiag(X_dev[b]), lambda: kern.Kzz(Zp))
+        # the package's own evaluation of one SVGP prediction's kernel terms (kernels.svgp_terms: what SVGP.build_predict
+        # calls -- one autograd node, the three launches on parallel streams)
+        kd, kuf, kuu = bk.svgp_terms(kern, Zp, X_dev[b], jitter=0.0)
         loss = (kuf * tens["G"]).sum() + (kd * tens["gd"]).sum() + (kuu * tens["Gu"]).sum()
         loss.backward()
         return torch.cat([t.grad.reshape(-1) for t in free] + [loss.detach().reshape(1)])

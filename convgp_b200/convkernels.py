@@ -107,6 +107,19 @@ class Conv(Kern):
         var, ls = self._base_params(Z.dtype)
         return ops.kuu(self._spec(Z.dtype), Z, var, ls)
 
+    def fused_terms(self, Z, X, diag_const=0.0, diag_param=None):
+        """(Kdiag(X) + diag_param, Kzx(Z, X), Kzz(Z) + (diag_const + diag_param) I) as ONE autograd node
+        (ops.kernel_terms), or None when this class evaluates the three with different arguments (per-channel
+        outputs, WeightedConvRBF's unweighted Kdiag)."""
+        t = type(self)
+        if (t.Kzx is not Conv.Kzx or t.Kdiag is not Conv.Kdiag or t.Kzz is not Conv.Kzz
+                or self._out_mode != _lib.OUT_SUM):
+            return None
+        var, ls = self._base_params(X.dtype)
+        dp = None if diag_param is None else diag_param.to(X.dtype).reshape(())
+        kzx, kd, kuu = ops.kernel_terms(self._spec(X.dtype), X, Z, self._weights(X.dtype), var, ls, diag_const, dp)
+        return kd, kzx, kuu
+
     # ------------------------------------------------------------------ host helpers
     def init_inducing(self, X, M, method="default"):  # convkernels.py:92-103
         X = np.asarray(X)

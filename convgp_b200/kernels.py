@@ -61,6 +61,9 @@ def svgp_terms(kern, Z, X, jitter=None):
     """(Kdiag(X), Kzx(Z, X), Kzz(Z) + jitter I): the three kernel evaluations of one SVGP prediction
     (misvgp.py:194-201, svsumgp.py:76-88; GPflow's SVGP.build_predict), on parallel streams (``concurrent``)."""
     jitter = settings.jitter_level if jitter is None else jitter
+    fused = _fused_terms(kern, Z, X, jitter)
+    if fused is not None:
+        return fused
 
     def kzz():
         K = kern.Kzz(Z)
@@ -68,6 +71,23 @@ def svgp_terms(kern, Z, X, jitter=None):
 
     kzx, kdiag, kmm = concurrent(lambda: kern.Kzx(Z, X), lambda: kern.Kdiag(X), kzz)
     return kdiag, kzx, kmm
+
+
+def _fused_terms(kern, Z, X, jitter):
+    """One patch kernel, alone or in a sum with White members (mnist.py:42, rectangles.py:44): one autograd node
+    for all three terms (Conv.fused_terms).  White contributes nothing to Kzx (White.K(Z, X) = 0), its variance to
+    Kdiag and to the diagonal of Kzz."""
+    if not (torch.cuda.is_available() and settings.device.type == "cuda"):
+        return None
+    members = kern.kern_list if isinstance(kern, Add) else [kern]
+    convs = [k for k in members if hasattr(k, "fused_terms")]
+    whites = [k for k in members if isinstance(k, White)]
+    if len(convs) != 1 or len(convs) + len(whites) != len(members):
+        return None
+    dp = None
+    for w in whites:
+        dp = w.variance() if dp is None else dp + w.variance()
+    return convs[0].fused_terms(Z, X, jitter, dp)
 
 
 class Kern(Parameterized):

@@ -174,6 +174,101 @@ class _Kuu(torch.autograd.Function):
         return None, dZ, dvar, dls, None
 
 
+class _KernelTerms(torch.autograd.Function):
+    """Kzx(Z, X), Kdiag(X) and Kzz(Z) + diag of ONE kernel in one autograd node (what an SVGP prediction evaluates:
+    misvgp.py:194-201, svsumgp.py:76-88): the three forward launches run on parallel streams, the parameter values are
+    read once, and the backward accumulates all three reverse passes into one packed gradient buffer
+    [dZ | dW | dvariance | dlengthscales] -- instead of three nodes with their own buffers, accumulations and
+    parameter transforms (about forty small torch kernels less per evaluation).  ``diag_const`` (jitter) and
+    ``diag_param`` (a 0-dim tensor: the variance of White members, or None) are added to the diagonal of Kzz, and
+    ``diag_param`` to Kdiag (White.Kdiag)."""
+
+    @staticmethod
+    def forward(ctx, spec, X, Z, W, variance, lengthscales, diag_const, diag_param):
+        from .kernels import concurrent
+        validate(spec, X=X, Z=Z, W=W, variance=variance, lengthscales=lengthscales)
+        X, Z, W, variance, lengthscales = map(_c, (X, Z, W, variance, lengthscales))
+        N, M = X.shape[0], Z.shape[0]
+        needs_grad = any(ctx.needs_input_grad[2:6])
+        L = _lib.lib()
+        Kuf = torch.empty((M, N), dtype=X.dtype, device=X.device)
+        Kd = torch.empty((N,), dtype=X.dtype, device=X.device)
+        Kuu = torch.empty((M, M), dtype=X.dtype, device=X.device)
+        with torch.cuda.device(X.device):
+            ws, nb = spec.workspace(N, M, X.device)
+            n_saved = L.cgp_kdiag_saved_elems(spec.ref(), N) if needs_grad and N > 0 else 0
+            saved = torch.empty(n_saved, dtype=X.dtype, device=X.device) if n_saved else None
+            ws2 = None if n_saved else spec.workspace(N, 0, X.device)
+
+            def f_kuf():
+                if N > 0 and M > 0:
+                    check(L.cgp_kuf_fwd(spec.ref(), N, M, ptr(X), ptr(Z), ptr(W), ptr(variance), ptr(lengthscales),
+                                        ptr(Kuf), ptr(ws), nb, stream_ptr()))
+
+            def f_kd():
+                if N == 0:
+                    return
+                if n_saved:
+                    check(L.cgp_kdiag_fwd_saved(spec.ref(), N, ptr(X), ptr(W), ptr(variance), ptr(lengthscales),
+                                                ptr(Kd), ptr(saved), n_saved, stream_ptr()))
+                else:
+                    check(L.cgp_kdiag_fwd(spec.ref(), N, ptr(X), ptr(W), ptr(variance), ptr(lengthscales), ptr(Kd),
+                                          ptr(ws2[0]), ws2[1], stream_ptr()))
+
+            def f_kuu():
+                check(L.cgp_kuu_fwd(spec.ref(), M, ptr(Z), ptr(variance), ptr(lengthscales), float(diag_const),
+                                    ptr(Kuu), stream_ptr()))
+
+            concurrent(f_kuf, f_kd, f_kuu)
+        if diag_param is not None:
+            Kuu.diagonal().add_(diag_param)
+            Kd.add_(diag_param)
+        ctx.spec, ctx.has_diag = spec, diag_param is not None
+        ctx.save_for_backward(X, Z, W, variance, lengthscales, saved)
+        return Kuf, Kd, Kuu
+
+    @staticmethod
+    def backward(ctx, G, gd, Gu):
+        from .kernels import concurrent
+        X, Z, W, variance, lengthscales, saved = ctx.saved_tensors
+        spec = ctx.spec
+        N, M = X.shape[0], Z.shape[0]
+        _, (dZ, dW, dvar, dls) = _grad_buffers(spec, Z, W, variance, lengthscales)
+        G, gd, Gu = _c(G), _c(gd), _c(Gu)
+        L = _lib.lib()
+        with torch.cuda.device(X.device):
+            ws, nb = spec.workspace(N, M, X.device)
+            ws2 = None if saved is not None else spec.workspace(N, 0, X.device)
+
+            def b_kuf():
+                if N > 0 and M > 0:
+                    check(L.cgp_kuf_bwd(spec.ref(), N, M, ptr(X), ptr(Z), ptr(W), ptr(variance), ptr(lengthscales),
+                                        ptr(G), ptr(dZ), ptr(dW), ptr(dvar), ptr(dls), ptr(ws), nb, stream_ptr()))
+
+            def b_kd():
+                if N == 0:
+                    return
+                if saved is not None:
+                    check(L.cgp_kdiag_bwd_saved(spec.ref(), N, ptr(variance), ptr(lengthscales), ptr(gd), ptr(saved),
+                                                saved.numel(), ptr(dW), ptr(dvar), ptr(dls), stream_ptr()))
+                else:
+                    check(L.cgp_kdiag_bwd(spec.ref(), N, ptr(X), ptr(W), ptr(variance), ptr(lengthscales), ptr(gd),
+                                          ptr(dW), ptr(dvar), ptr(dls), ptr(ws2[0]), ws2[1], stream_ptr()))
+
+            def b_kuu():
+                check(L.cgp_kuu_bwd(spec.ref(), M, ptr(Z), ptr(variance), ptr(lengthscales), ptr(Gu), ptr(dZ),
+                                    ptr(dvar), ptr(dls), stream_ptr()))
+
+            concurrent(b_kuf, b_kd, b_kuu)  # all three accumulate (atomics) into the one packed buffer
+        d_diag = (Gu.diagonal().sum() + gd.sum()) if ctx.has_diag else None
+        return None, None, dZ, dW, dvar, dls, None, d_diag
+
+
+def kernel_terms(spec, X, Z, W, variance, lengthscales, diag_const=0.0, diag_param=None):
+    """(Kzx(Z, X), Kdiag(X) + diag_param, Kzz(Z) + (diag_const + diag_param) I) in one autograd node."""
+    return _KernelTerms.apply(spec, X, Z, W, variance, lengthscales, float(diag_const), diag_param)
+
+
 def kuf(spec, X, Z, W, variance, lengthscales):
     """Kzx(Z, X): (M, N) or (M, N, C)."""
     return _Kuf.apply(spec, X, Z, W, variance, lengthscales)
