@@ -641,7 +641,7 @@ def measure_e2e(ctx, cfg, dtype_name, hp, inp, tens, steps):
 def _traffic(dtype_name, kernel):
     """DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture (latest first)."""
     try:
-        for name in ("r2_traffic.json", "r1z_traffic.json", "r1_traffic.json"):
+        for name in ("r2z_traffic.json", "r1z_traffic.json", "r1_traffic.json"):
             path = os.path.join(ROOT, "profiles", name)
             if os.path.exists(path):
                 v = json.load(open(path)).get(dtype_name, {}).get(kernel)

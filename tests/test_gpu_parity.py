@@ -193,7 +193,9 @@ def test_full_size_cifar_shapes_f32(idx):
     X, Z = as_tensor(case.X, torch.float32), as_tensor(case.Z, torch.float32)
     spec = k._spec(torch.float32)
     fam = [_lib.lib().cgp_kernel_family(spec.ref(), X.shape[0], Z.shape[0], w).decode() for w in range(3)]
-    if idx == 0:
+    if os.environ.get("CGP_TEST_OPTIONS"):
+        pass  # a forced family (tests/test_gpu_variants.py): whatever it dispatches to must pass the checks below
+    elif idx == 0:
         assert fam == ["umma16"] * 3, fam  # no float32 BASELINE configuration on the mma.sync family
     else:  # 2352 patches of a 3-plane image: only the Kuf forward operands fit shared memory
         assert fam[0] == "umma16", fam
