@@ -354,29 +354,39 @@ static int run_umma_rowsum(int mode, const cgp_kernel_desc* d, const Geo& g, int
 //   fast mode 2: colour-patch layout with one RBF per channel (cifar.py:33-41): k = sum_g k_g where k_g only sees colour
 //                plane g of the image and elements g::C of an inducing patch, so the kernel is the SUM over g of the
 //                single-channel problem on plane g: one launch per group, accumulating into the same outputs.
+//   per-channel outputs (fast mode 1 + CGP_OUT_PER_CHANNEL, misvgp.py:51-73): one group per channel too, with a
+//                shared RBF and inducing set, weights W[c, :] and its own output slot.
 struct U16View {  // what one launch sees
-  int C, Cx, choff;   // staged channels, channels in memory, staged channel (C == 1 < Cx)
+  int C, Cx, choff;   // staged channels, channels in memory, first staged channel (C == 1 < Cx)
   int P, Pc, D;       // patches of the pairing domain, positions per plane, elements per patch of the group
   int zrow, zs, zo;   // Z[m * zrow + d * zs + zo]
+  int G, gv, gw, os;  // groups of the launch; per group: variance / lengthscale / Z-offset stride, weight stride,
+                      // output elements per (m, n)
 };
-static int u16_groups(const cgp_kernel_desc* d, int mode) { return mode == 2 ? d->C : 1; }
-static U16View u16_view(const cgp_kernel_desc* d, const Geo& g, int mode, int gi) {
+static bool u16_per_channel(const cgp_kernel_desc* d, int mode) {
+  return mode == 1 && d->out_mode == CGP_OUT_PER_CHANNEL && d->C > 1;
+}
+static U16View u16_view(const cgp_kernel_desc* d, const Geo& g, int mode) {
   U16View v;
   if (mode == 2) {
-    v.C = 1; v.Cx = d->C; v.choff = gi; v.P = g.Pc; v.Pc = g.Pc; v.D = d->ph * d->pw;
-    v.zrow = g.D; v.zs = d->C; v.zo = gi;
+    v.C = 1; v.Cx = d->C; v.choff = 0; v.P = g.Pc; v.Pc = g.Pc; v.D = d->ph * d->pw;
+    v.zrow = g.D; v.zs = d->C; v.zo = 0; v.G = d->C; v.gv = 1; v.gw = 0; v.os = 1;
+  } else if (u16_per_channel(d, mode)) {
+    v.C = 1; v.Cx = d->C; v.choff = 0; v.P = g.Pc; v.Pc = g.Pc; v.D = g.D;
+    v.zrow = g.D; v.zs = 1; v.zo = 0; v.G = d->C; v.gv = 0; v.gw = g.Pc; v.os = d->C;
   } else {
     v.C = d->C; v.Cx = d->C; v.choff = 0; v.P = g.P; v.Pc = g.Pc; v.D = g.D; v.zrow = g.D; v.zs = 1; v.zo = 0;
+    v.G = 1; v.gv = 0; v.gw = 0; v.os = 1;
   }
   return v;
 }
 static bool u16_mode_ok(const cgp_kernel_desc* d, int mode) {
-  return (mode == 1 || mode == 2) && d->dtype == CGP_F32 && d->out_mode != CGP_OUT_PER_CHANNEL;
+  return (mode == 1 || mode == 2) && d->dtype == CGP_F32 && (d->out_mode != CGP_OUT_PER_CHANNEL || mode == 1);
 }
 
 static bool umma16_kuf_plan(const cgp_kernel_desc* d, const Geo& g, int mode, int M, int* nbuf_out) {
   if (!u16_mode_ok(d, mode)) return false;
-  const U16View v = u16_view(d, g, mode, 0);
+  const U16View v = u16_view(d, g, mode);
   const int KP = umma16::pad_k(v.D), TN = 192;
   const int n_pt = (v.P + TN - 1) / TN, n_zt = (M + umma16::TM - 1) / umma16::TM;
   for (int nbuf = 3; nbuf >= 2; --nbuf)
@@ -396,11 +406,11 @@ static int run_umma16_kuf_fwd(const cgp_kernel_desc* d, const Geo& g, int mode, 
   int dev = 0;
   CGP_CUDA_CHECK(cudaGetDevice(&dev));
   {  // one launch: CTA b works on RBF group b % G
-    const int G = u16_groups(d, mode);
-    const U16View v = u16_view(d, g, mode, 0);
+    const U16View v = u16_view(d, g, mode);
+    const int G = v.G;
     umma16::Params p;
     memset(&p, 0, sizeof(p));
-    p.G = G;
+    p.G = G; p.gv = v.gv; p.gw = v.gw; p.os = v.os;
     p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
     p.ls = (const float*)ls; p.out = (float*)out;
     p.N = N; p.M = M; p.H = d->H; p.Wd = d->W; p.C = v.C; p.Hout = g.Hout; p.Wout = g.Wout; p.Pc = v.Pc; p.P = v.P; p.D = v.D;
@@ -449,7 +459,7 @@ static int run_umma16_kuf_fwd(const cgp_kernel_desc* d, const Geo& g, int mode, 
 // Kuf backward (umma16.cuh kuf_bwd_kernel): two row tiles, one patch tile and a range of images per CTA.
 static bool umma16_bwd_plan(const cgp_kernel_desc* d, const Geo& g, int mode) {
   if (!u16_mode_ok(d, mode)) return false;
-  const U16View v = u16_view(d, g, mode, 0);
+  const U16View v = u16_view(d, g, mode);
   constexpr int TN = 192;
   const int n_pt = (v.P + TN - 1) / TN;
   return v.D + 2 <= 32 &&
@@ -464,11 +474,11 @@ static int run_umma16_kuf_bwd(const cgp_kernel_desc* d, const Geo& g, int mode, 
   int dev = 0;
   CGP_CUDA_CHECK(cudaGetDevice(&dev));
   {  // one launch: CTA b works on RBF group b % G
-    const int Gr = u16_groups(d, mode);
-    const U16View v = u16_view(d, g, mode, 0);
+    const U16View v = u16_view(d, g, mode);
+    const int Gr = v.G;
     umma16::BwdParams p;
     memset(&p, 0, sizeof(p));
-    p.G = Gr;
+    p.G = Gr; p.gv = v.gv; p.gw = v.gw; p.os = v.os;
     p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
     p.ls = (const float*)ls; p.G_up = (const float*)G; p.dZ = (float*)dZ; p.dW = W ? (float*)dW : nullptr;
     p.dvar = (float*)dvar; p.dls = (float*)dls;
@@ -517,7 +527,7 @@ static int run_umma16_kuf_bwd(const cgp_kernel_desc* d, const Geo& g, int mode, 
 // Kdiag forward (umma16.cuh kdiag_fwd_kernel): one pairing domain per image, tiles on or above the diagonal only.
 static bool umma16_kdiag_plan(const cgp_kernel_desc* d, const Geo& g, int mode, int* nbuf_out) {
   if (!u16_mode_ok(d, mode)) return false;
-  const U16View v = u16_view(d, g, mode, 0);
+  const U16View v = u16_view(d, g, mode);
   const int KD = umma16::pad_kd(v.D), nt = (v.P + 127) / 128;
   for (int nbuf = 2; nbuf >= 1; --nbuf)
     if (umma16::kd_smem_plan(KD, d->H * d->W * v.C, nt * 128, nbuf).total <= 227 * 1024) {
@@ -537,11 +547,11 @@ static int run_umma16_kdiag(const cgp_kernel_desc* d, const Geo& g, int mode, in
   int dev = 0;
   CGP_CUDA_CHECK(cudaGetDevice(&dev));
   {  // one launch: CTA b works on RBF group b % G
-    const int G = u16_groups(d, mode);
-    const U16View v = u16_view(d, g, mode, 0);
+    const U16View v = u16_view(d, g, mode);
+    const int G = v.G;
     umma16::KdParams p;
     memset(&p, 0, sizeof(p));
-    p.G = G;
+    p.G = G; p.gv = v.gv; p.gw = v.gw; p.os = v.os;
     p.X = (const float*)X; p.Wt = (const float*)W; p.var = (const float*)var; p.ls = (const float*)ls;
     p.out = (float*)out; p.save = (float*)save;
     if (save) {

@@ -68,8 +68,12 @@ struct Params {
   int N, M, H, Wd, C, Hout, Wout, Pc, P, D;
   int Cx, choff;      // channels of the image in memory and the staged channel when C == 1 < Cx (else Cx == C, choff = 0)
   int zrow, zs, zo;   // element d of inducing row m is Z[m * zrow + d * zs + zo] (planar: D, 1, 0; colour group g: C D, C, g)
-  int G;              // RBF groups handled by this launch: CTA b works on group b % G (var[g], ls[g], channel choff + g,
-                      // Z offset zo + g) and shares that group's units with the other CTAs of the group
+  int G;              // groups handled by this launch: CTA b works on group g = b % G -- image plane choff + g -- and
+                      // shares that group's units with the other CTAs of the group.  A group is an RBF member of the
+                      // colour-patch additive kernel (gv = 1: var[g], ls[g], Z offset zo + g) or a channel of the
+                      // per-channel kernel (misvgp.py:51-73; gv = 0: shared RBF and Z, weights W + g gw, output
+                      // element [(m N + n) os + g])
+  int gv, gw, os;
   int n_pt;    // patch column tiles per image
   int n_zt;    // inducing row tiles
   int Mpad;    // n_zt * TM
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = blockIdx.x % p.G, cta = blockIdx.x / p.G, ncta = ((int)gridDim.x - grp + p.G - 1) / p.G;
-  const int choff = p.choff + grp, zo = p.zo + grp;
+  const int choff = p.choff + grp, zo = p.zo + grp * p.gv;
   const long long lo = p.n_units * cta / ncta;
   const long long hi = p.n_units * (cta + 1) / ncta;
   const int nun = (int)(hi - lo);
@@ -279,12 +283,12 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
     const int zbytes = p.M * p.zrow * 4;
     for (int o = tid * 128; o < zbytes; o += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(zb + o));
   }
-  const float lsv = p.ls[grp], sig2 = p.var[grp];
+  const float lsv = p.ls[grp * p.gv], sig2 = p.var[grp * p.gv];
 
   for (int i = tid; i < Ppad; i += kThreads) {
     const int q = min(i, p.P - 1);  // rows past the last patch repeat it (finite exponents); their weight is zero
     const int c = q / p.Pc, pos = q % p.Pc;
-    w[i] = i < p.P ? (p.Wt ? p.Wt[i] : 1.f) : 0.f;
+    w[i] = i < p.P ? (p.Wt ? p.Wt[(size_t)grp * p.gw + i] : 1.f) : 0.f;
     org[i] = ((pos / p.Wout) * p.Wd + (pos % p.Wout)) * p.C + c;
   }
   for (int i = tid; i < 3 * p.Mpad; i += kThreads) racc[i] = 0.f;
@@ -462,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) kuf_fwd_kernel(const Params p) {
       for (int m = et; m < p.M; m += kEpi) {
         const float v = (racc[m] + racc[p.Mpad + m]) + racc[2 * p.Mpad + m];
         racc[m] = racc[p.Mpad + m] = racc[2 * p.Mpad + m] = 0.f;
-        atomicAdd(p.out + (size_t)m * p.N + n, v * s_kuf);
+        atomicAdd(p.out + ((size_t)m * p.N + n) * p.os + (p.os > 1 ? grp : 0), v * s_kuf);
       }
       named_sync(2, kEpi);
     };
@@ -567,7 +571,7 @@ struct KdParams {
   float* out;   // Kdiag (N), zero-initialised
   float* save;  // [N * P] row sums, [N] v, [N] v2 (zero-initialised) or nullptr
   int N, H, Wd, C, Wout, Pc, P;
-  int Cx, choff, G;  // see Params (group g also uses save_v + 2 g N, save_v2 + 2 g N)
+  int Cx, choff, G, gv, gw, os;  // see Params (group g also uses save_v + 2 g N, save_v2 + 2 g N)
   float* save_v;  // [N] sum_q w_q r and [N] sum w w k * exponent of this launch's RBF group
   float* save_v2;
   int rscale;     // 1: the saved row sums carry the group's variance (several groups accumulate into them)
@@ -685,11 +689,11 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
   __syncthreads();
   if (warp < kdProd / 32 && nun > 0)
     fetch_image_async(raw0, p.X + (size_t)n_first * HWC * (p.Cx / p.C), HWC, tid, kdProd, &img_bar[0], p.Cx / p.C, choff);
-  const float lsv = p.ls[grp], sig2 = p.var[grp];
+  const float lsv = p.ls[grp * p.gv], sig2 = p.var[grp * p.gv];
   for (int i = tid; i < Rpad; i += kdThreads) {
     const int q = min(i, p.P - 1);
     const int c = q / p.Pc, pos = q % p.Pc;
-    w[i] = i < p.P ? (p.Wt ? p.Wt[i] : 1.f) : 0.f;
+    w[i] = i < p.P ? (p.Wt ? p.Wt[(size_t)grp * p.gw + i] : 1.f) : 0.f;
     org[i] = ((pos / p.Wout) * p.Wd + (pos % p.Wout)) * p.C + c;
   }
   for (int i = tid; i < 2 * Rpad; i += kdThreads) racc[i] = racc2[i] = 0.f;
@@ -847,7 +851,7 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
       const float v = epi_sum(v1);
       const float vv = epi_sum(v2);
       if (et == 0) {
-        atomicAdd(p.out + n, v * s_kd);
+        atomicAdd(p.out + (size_t)n * p.os + (p.os > 1 ? grp : 0), v * s_kd);
         if (p.save) {
           atomicAdd(p.save_v + (size_t)(2 * grp) * p.N + n, v);
           atomicAdd(p.save_v2 + (size_t)(2 * grp) * p.N + n, vv);
@@ -998,7 +1002,7 @@ struct BwdParams {
   float* dvar;
   float* dls;
   int N, M, H, Wd, C, Wout, Pc, P;
-  int Cx, choff, zrow, zs, zo, G;  // see Params (group g accumulates dvar[g], dls[g])
+  int Cx, choff, zrow, zs, zo, G, gv, gw, os;  // see Params (group g accumulates dvar[g gv], dls[g gv], dW + g gw)
   int n_pt, n_zt, n_rp, S;  // patch tiles, row tiles, row-tile pairs, image shares per (row-tile pair, patch tile)
   float Pn;
   long long* trace;
@@ -1091,7 +1095,8 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kg = blockIdx.x % p.G, rest = blockIdx.x / p.G;  // RBF group of this CTA
-  const int choff = p.choff + kg, zo = p.zo + kg;
+  const int choff = p.choff + kg, zo = p.zo + kg * p.gv;
+  const int gofs = p.os > 1 ? kg : 0;  // upstream gradient element [(m N + n) os + g], as Kuf
   const int grp = rest / p.S, share = rest % p.S;
   const int rp = grp / p.n_pt, jt = grp % p.n_pt;  // row-tile pair, patch tile
   const int nrt = min(2, p.n_zt - 2 * rp);         // row tiles of this CTA
@@ -1108,11 +1113,11 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
   if (warp >= kbProdWarp0 && warp < kbIssuerWarp && nimg > 0)
     fetch_image_async(raw0, p.X + (size_t)n_lo * HWC * (p.Cx / p.C), HWC, tid - kbProdWarp0 * 32, kbProd, &img_bar[0],
                       p.Cx / p.C, choff);
-  const float lsv = p.ls[kg], sig2 = p.var[kg];
+  const float lsv = p.ls[kg * p.gv], sig2 = p.var[kg * p.gv];
   for (int i = tid; i < Ppad; i += kbThreads) {
     const int q = min(i, p.P - 1);
     const int c = q / p.Pc, pos = q % p.Pc;
-    w[i] = i < p.P ? (p.Wt ? p.Wt[i] : 1.f) : 0.f;
+    w[i] = i < p.P ? (p.Wt ? p.Wt[(size_t)kg * p.gw + i] : 1.f) : 0.f;
     org[i] = ((pos / p.Wout) * p.Wd + (pos % p.Wout)) * p.C + c;
   }
   // (integer divisions only here: in the unit loop their I2F / MUFU.RCP / F2I would queue behind the epilogue's ex2)
@@ -1381,8 +1386,8 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
     {
       float gm = 0.f, wm = 0.f;
       for (int n = n_lo + third; n < n_hi; n += 3) {
-        if (va) gm = fmaxf(gm, fabsf(p.G_up[(size_t)ma * p.N + n]));
-        if (vb) gm = fmaxf(gm, fabsf(p.G_up[(size_t)mb * p.N + n]));
+        if (va) gm = fmaxf(gm, fabsf(p.G_up[((size_t)ma * p.N + n) * p.os + gofs]));
+        if (vb) gm = fmaxf(gm, fabsf(p.G_up[((size_t)mb * p.N + n) * p.os + gofs]));
       }
       for (int i = et; i < TN; i += kbEpi) wm = fmaxf(wm, fabsf(w[c0p + i]));
 #pragma unroll
@@ -1415,14 +1420,14 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
     float dwacc[CW];  // these rows' sum over the CTA's images of c0, for each of this warp's 64 columns
 #pragma unroll
     for (int t = 0; t < CW; ++t) dwacc[t] = 0.f;
-    float ga = (nun > 0 && va) ? p.G_up[(size_t)ma * p.N + n_lo] : 0.f;
-    float gb = (nun > 0 && vb) ? p.G_up[(size_t)mb * p.N + n_lo] : 0.f;
+    float ga = (nun > 0 && va) ? p.G_up[((size_t)ma * p.N + n_lo) * p.os + gofs] : 0.f;
+    float gb = (nun > 0 && vb) ? p.G_up[((size_t)mb * p.N + n_lo) * p.os + gofs] : 0.f;
     for (int u = 0; u < nun; ++u) {
       const int k = nrt == 2 ? u >> 1 : u, rt = u - k * nrt;
       const float Gm = (rt == 0 ? ga : gb) * gs;
       if (rt == nrt - 1 && k + 1 < nimg) {  // next image's upstream gradients, a unit ahead
-        if (va) ga = p.G_up[(size_t)ma * p.N + n_lo + k + 1];
-        if (vb) gb = p.G_up[(size_t)mb * p.N + n_lo + k + 1];
+        if (va) ga = p.G_up[((size_t)ma * p.N + n_lo + k + 1) * p.os + gofs];
+        if (vb) gb = p.G_up[((size_t)mb * p.N + n_lo + k + 1) * p.os + gofs];
       }
       mbar_wait(&g1_done[u & 1], (u >> 1) & 1);
       if (et == 0) CGP_TU(6, u);
@@ -1480,7 +1485,7 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
       named_sync(2, kbEpi);
       for (int c = et; c < TN; c += kbEpi) {
         const float v = (cacc[c] + cacc[TN + c]) + (cacc[2 * TN + c] + cacc[3 * TN + c]);
-        if (c0p + c < p.P) atomicAdd(p.dW + c0p + c, sig2 * inv_cscale * v);
+        if (c0p + c < p.P) atomicAdd(p.dW + (size_t)kg * p.gw + c0p + c, sig2 * inv_cscale * v);
       }
     }
     float s0row = 0.f, slrow = 0.f;
@@ -1520,8 +1525,8 @@ __global__ void __launch_bounds__(kbThreads, 1) kuf_bwd_kernel(const BwdParams p
           a0 += red[k2];
           a2 += red[16 + k2];
         }
-        if (p.dvar) atomicAdd(p.dvar + kg, a0);
-        if (p.dls) atomicAdd(p.dls + kg, -2.f * sig2 / lsv * a2 / 1.4426950408889634f);
+        if (p.dvar) atomicAdd(p.dvar + kg * p.gv, a0);
+        if (p.dls) atomicAdd(p.dls + kg * p.gv, -2.f * sig2 / lsv * a2 / 1.4426950408889634f);
       }
     }
   }

@@ -179,11 +179,11 @@ def test_full_size_cifar_shapes_f64(idx):
     assert rel_err(kd, sub["kdiag"]) < 1e-10
 
 
-@pytest.mark.parametrize("idx", [0, 1], ids=["cfg5_full", "cifar_wconv_full"])
+@pytest.mark.parametrize("idx", [0, 1, 2], ids=["cfg5_full", "cifar_wconv_full", "cifar_multi_full"])
 def test_full_size_cifar_shapes_f32(idx):
     """The same full-size CIFAR geometries in float32: config 5 (three RBF groups in one launch of each umma16 kernel,
-    M = 1000 with a two-deep patch-tile ring, a single-buffered 784-patch Kdiag image) and the planar 3-channel kernel
-    (one 2352-patch pairing domain).  Values against the committed float64 sub-samples (1e-4); gradients against the
+    M = 1000 with a two-deep patch-tile ring, a single-buffered 784-patch Kdiag image), the planar 3-channel kernel
+    (one 2352-patch pairing domain) and the per-channel kernel of `cifar.py -k multi` (one group per channel).  Values against the committed float64 sub-samples (1e-4); gradients against the
     float64 CUDA path on the same inputs, repeated (asynchronous pipelines: a race shows up intermittently)."""
     import os
     from convgp_b200 import _lib
@@ -195,7 +195,7 @@ def test_full_size_cifar_shapes_f32(idx):
     fam = [_lib.lib().cgp_kernel_family(spec.ref(), X.shape[0], Z.shape[0], w).decode() for w in range(3)]
     if os.environ.get("CGP_TEST_OPTIONS"):
         pass  # a forced family (tests/test_gpu_variants.py): whatever it dispatches to must pass the checks below
-    elif idx == 0:
+    elif idx in (0, 2):  # colour groups / per-channel outputs: one group per channel in one launch
         assert fam == ["umma16"] * 3, fam  # no float32 BASELINE configuration on the mma.sync family
     else:  # 2352 patches of a 3-plane image: only the Kuf forward operands fit shared memory
         assert fam[0] == "umma16", fam

@@ -174,7 +174,7 @@ def test_options_api_and_family_query():
     for which in (0, 1, 2):  # Kuf forward / backward, Kdiag forward: the two-fp16-term tcgen05 family by default
         assert L.cgp_kernel_family(f32.ref(), 200, 750, which) == b"umma16"
     # planar colour images (Conv with colour_channels = 3: one pairing domain) take the same family when the
-    # shared-memory plan fits; per-channel outputs do not
+    # shared-memory plan fits
     rgb = _lib.Spec(torch.float32, 16, 16, 3, 5, 5, _lib.LAYOUT_PLANAR, _lib.OUT_SUM, 1, False, False)
     assert all(L.cgp_kernel_family(rgb.ref(), 30, 100, w) == b"umma16" for w in (0, 1, 2))
     # config 5: colour patches with one RBF per channel (cifar.py:33-41) = one launch whose CTAs split over the groups
@@ -183,8 +183,11 @@ def test_options_api_and_family_query():
     assert [L.cgp_kernel_family(cifar.ref(), 30, 1000, w) for w in (0, 1, 2, 3)] == \
         [b"umma16", b"umma16", b"umma16", b"saved-row-sums"]
     assert L.cgp_kdiag_saved_elems(cifar.ref(), 30) == 30 * (784 + 2 * 3)
+    # per-channel outputs (WeightedMultiChannelConvGP): one group per channel in the same launches; its Kdiag backward
+    # (no saved-row-sum variant for (N, C) outputs) recomputes on the mma.sync family
     multi = _lib.Spec(torch.float32, 16, 16, 3, 5, 5, _lib.LAYOUT_PLANAR, _lib.OUT_PER_CHANNEL, 1, False, False)
-    assert L.cgp_kernel_family(multi.ref(), 30, 100, 0) != b"umma16"
+    assert [L.cgp_kernel_family(multi.ref(), 30, 100, w) for w in (0, 1, 2, 3)] == \
+        [b"umma16", b"umma16", b"umma16", b"hmma32"]
     _lib.set_option("kuf_fwd_f32", 2)
     _lib.set_option("kuf_bwd_f32", 2)
     try:
