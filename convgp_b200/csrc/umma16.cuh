@@ -27,7 +27,9 @@
 //
 // Range: fp16 overflows above 65504, so this family needs c2 |patch|^2 < 6e4, i.e. |patch| / l < 288 (pixel data
 // in [0, 1] with 5x5 patches: l > 0.018).  Outside that range the result is NaN (inf - inf), never a silently
-// wrong finite number; the 3xTF32 family (umma32.cuh, option *_f32 = 2) has float32's range.
+// wrong finite number; the 3xTF32 family (umma32.cuh, option *_f32 = 2) has float32's range
+// (and float32's accuracy for the expanded distance, which degrades as c2 |patch|^2 grows -- as for the reference's
+// float32 TensorFlow graph); tests/test_gpu_range.py pins both.
 #pragma once
 #include "umma32.cuh"
 
