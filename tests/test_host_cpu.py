@@ -173,6 +173,12 @@ def test_options_api_and_family_query():
     assert L.cgp_kernel_family(f64.ref(), 200, 750, 0) == b"dmma64"
     for which in (0, 1, 2):  # Kuf forward / backward, Kdiag forward: the two-fp16-term tcgen05 family by default
         assert L.cgp_kernel_family(f32.ref(), 200, 750, which) == b"umma16"
+    # every float32 BASELINE configuration is on the tcgen05 kind::f16 family (cfg 1: 3x3 patches, M = 16; cfg 2: M = 50;
+    # cfg 3 / 4: M = 750; cfg 5 below)
+    cfg1 = _lib.Spec(torch.float32, 28, 28, 1, 3, 3, 0, 0, 1, False, False)
+    for spec, n, m in ((cfg1, 100, 16), (f32, 100, 50), (f32, 200, 750)):
+        assert [L.cgp_kernel_family(spec.ref(), n, m, w) for w in (0, 1, 2, 3)] == \
+            [b"umma16", b"umma16", b"umma16", b"saved-row-sums"]
     # planar colour images (Conv with colour_channels = 3: one pairing domain) take the same family when the
     # shared-memory plan fits
     rgb = _lib.Spec(torch.float32, 16, 16, 3, 5, 5, _lib.LAYOUT_PLANAR, _lib.OUT_SUM, 1, False, False)
