@@ -598,8 +598,10 @@ __host__ __device__ inline KdSmem kd_smem_plan(int KD, int HWC, int Rpad, int nb
   o += 3 * al16(HWC * 4);
   s.xs = o;
   o += 2 * al16(HWC * 4);
-  s.en = o;  // four-deep: the epilogue of image k still reads its norms while the producers are two images ahead
-  o += 4 * Rpad * 4;
+  // eight-deep: the producers run up to nbuf (<= 2) images ahead of the MMAs and the MMAs up to four units -- four
+  // IMAGES when an image is a single unit -- ahead of the epilogue, which still reads the norms of its image
+  s.en = o;
+  o += 8 * Rpad * 4;
   s.w = o;
   o += Rpad * 4;
   s.org = o;
@@ -753,7 +755,7 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
       mbar_wait(&img_bar[k % 3], (k / 3) & 1);
       const float* raw = raw0 + (k % 3) * raw_stride;
       uint32_t* xs = xs0 + (k & 1) * raw_stride;
-      float* en = en0 + (k & 3) * Rpad;
+      float* en = en0 + (k & 7) * Rpad;
       for (int i = pt; i < HWC; i += kdProd) xs[i] = split_f16(raw[i] * sc);
       for (int q = pt; q < Rpad; q += kdProd) {
         const float* base = raw + org[q];
@@ -867,7 +869,7 @@ __global__ void __launch_bounds__(kdThreads, 1) kdiag_fwd_kernel(const KdParams 
     bool cs_dirty = false;
     int n = n_first, i = i_first, j = j_first, k = 0;
     for (int u = 0; u < nun; ++u) {
-      const float* en = en0 + (k & 3) * Rpad;
+      const float* en = en0 + (k & 7) * Rpad;
       const bool wide = j != nt - 1 || p.NL == 128, mirrored = j > i;
       const int cw = wide ? 64 : 32;            // this warp's columns of the unit
       const int c0 = j * 128 + half * cw;       // first patch column
