@@ -384,16 +384,20 @@ static bool u16_mode_ok(const cgp_kernel_desc* d, int mode) {
   return (mode == 1 || mode == 2) && d->dtype == CGP_F32 && (d->out_mode != CGP_OUT_PER_CHANNEL || mode == 1);
 }
 
-static bool umma16_kuf_plan(const cgp_kernel_desc* d, const Geo& g, int mode, int M, int* nbuf_out) {
+// The inducing set is resident in shared memory: when all of it does not fit, the rows are processed in blocks of
+// *mblk_out (a multiple of 128), one launch per block.
+static bool umma16_kuf_plan(const cgp_kernel_desc* d, const Geo& g, int mode, int M, int* nbuf_out, int* mblk_out = nullptr) {
   if (!u16_mode_ok(d, mode)) return false;
   const U16View v = u16_view(d, g, mode);
   const int KP = umma16::pad_k(v.D), TN = 192;
-  const int n_pt = (v.P + TN - 1) / TN, n_zt = (M + umma16::TM - 1) / umma16::TM;
-  for (int nbuf = 3; nbuf >= 2; --nbuf)
-    if (umma16::kuf_smem_plan(KP, TN, d->H * d->W * v.C, n_pt * TN, n_zt * umma16::TM, nbuf).total <= 227 * 1024) {
-      if (nbuf_out) *nbuf_out = nbuf;
-      return true;
-    }
+  const int n_pt = (v.P + TN - 1) / TN, Mpad = (M + umma16::TM - 1) / umma16::TM * umma16::TM;
+  for (int rows = Mpad; rows >= umma16::TM; rows -= umma16::TM)
+    for (int nbuf = 3; nbuf >= 2; --nbuf)
+      if (umma16::kuf_smem_plan(KP, TN, d->H * d->W * v.C, n_pt * TN, rows, nbuf).total <= 227 * 1024) {
+        if (nbuf_out) *nbuf_out = nbuf;
+        if (mblk_out) *mblk_out = rows;
+        return true;
+      }
   return false;
 }
 
@@ -401,18 +405,20 @@ static int run_umma16_kuf_fwd(const cgp_kernel_desc* d, const Geo& g, int mode, 
                               const void* Z, const void* W, const void* var, const void* ls, void* out,
                               cudaStream_t st) {
   constexpr int TN = 192;
-  int nbuf = 0;
-  if (!umma16_kuf_plan(d, g, mode, M, &nbuf)) { set_error("umma16 kuf: shared-memory plan does not fit"); return CGP_ERR_UNSUPPORTED; }
+  int nbuf = 0, mblk = 0;
+  if (!umma16_kuf_plan(d, g, mode, M, &nbuf, &mblk)) { set_error("umma16 kuf: shared-memory plan does not fit"); return CGP_ERR_UNSUPPORTED; }
   int dev = 0;
   CGP_CUDA_CHECK(cudaGetDevice(&dev));
-  {  // one launch: CTA b works on RBF group b % G
+  const int M_all = M;
+  for (int m0 = 0; m0 < M_all; m0 += mblk) {  // one launch per block of inducing rows: CTA b works on RBF group b % G
     const U16View v = u16_view(d, g, mode);
     const int G = v.G;
+    M = std::min(mblk, M_all - m0);
     umma16::Params p;
     memset(&p, 0, sizeof(p));
     p.G = G; p.gv = v.gv; p.gw = v.gw; p.os = v.os;
-    p.X = (const float*)X; p.Z = (const float*)Z; p.Wt = (const float*)W; p.var = (const float*)var;
-    p.ls = (const float*)ls; p.out = (float*)out;
+    p.X = (const float*)X; p.Z = (const float*)Z + (size_t)m0 * v.zrow; p.Wt = (const float*)W; p.var = (const float*)var;
+    p.ls = (const float*)ls; p.out = (float*)out + (size_t)m0 * N * v.os;
     p.N = N; p.M = M; p.H = d->H; p.Wd = d->W; p.C = v.C; p.Hout = g.Hout; p.Wout = g.Wout; p.Pc = v.Pc; p.P = v.P; p.D = v.D;
     p.Cx = v.Cx; p.choff = v.choff; p.zrow = v.zrow; p.zs = v.zs; p.zo = v.zo;
     p.n_pt = (v.P + TN - 1) / TN;
